@@ -1,0 +1,304 @@
+// r3g_attention: O = softmax(Q K^T * scale) V for head_dim 64, no mask -- flash-attention forward on tcgen05.
+//
+// One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so that one CTA's
+// softmax (MUFU-bound) overlaps the other's MMAs.
+//   warps 0..3  softmax / correction / epilogue: thread t owns query row t (TMEM lane t): row max and row
+//               sum need no shuffles; P is written as fp16 into a 128B-swizzled K-major smem tile
+//   warp 4      TMA producer: Q once, then K and V tiles (128 x 64) through 2-deep rings
+//   warp 5      MMA issuer:  S = Q K^T  (M128 N128 K16 x4, accumulator in TMEM)
+//                            O_j = P V  (M128 N64  K16 x8, V consumed MN-major straight from its row-major tile)
+// O_j is accumulated in registers with the usual running-max rescale, so TMEM is never read-modify-written.
+// Call sites replaced: F.scaled_dot_product_attention in hunyuan3ddit.py:33-36 (L = 4442 joint txt+img tokens),
+// attention_blocks.py:328 (ShapeVAE, L = 3072), attention_processors.py:29-32 (geo-decoder cross attention,
+// Lk = 3072), vggt/layers/attention.py:61.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "r3g_internal.h"
+#include "r3g_ptx.cuh"
+
+namespace {
+
+using namespace r3g;
+
+constexpr int kD = 64;
+constexpr int kBQ = 128;
+constexpr int kBKV = 128;
+constexpr int kKVStages = 2;
+constexpr int kThreads = 192;
+constexpr int kTileBytes = 128 * kD * 2;          // 16 KB: Q, K and V tiles
+constexpr int kPBytes = kBQ * kBKV * 2;           // 32 KB
+constexpr int kTilesBytes = kTileBytes * (1 + 2 * kKVStages) + kPBytes;  // 112 KB
+constexpr int kSmemBytes = kTilesBytes + 1024;    // + alignment slack, which also hosts the barriers
+constexpr uint32_t kTmemCols = 256;               // S: 128 columns, O_j: 64 columns
+constexpr uint32_t kTmemS = 0, kTmemO = 128;
+
+struct AttnParams {
+  __half* o;
+  int64_t o_sb, o_sh, o_sl;
+  int Lq, Lk;
+  float scale_log2;  // scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
+  const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
+  // barriers live in whichever end of the 1 KB slack is free
+  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kTileBytes;
+  uint8_t* sP = sV + kKVStages * kTileBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* v_full = k_full + kKVStages;
+  uint64_t* k_empty = v_full + kKVStages;
+  uint64_t* v_empty = k_empty + kKVStages;
+  uint64_t* s_full = v_empty + kKVStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + kBKV - 1) / kBKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        tma_load_4d(sV + st * kTileBytes, &tmap_v, &v_full[st], 0, j * kBKV, h, b, kEvictLast);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);  // B = V, MN-major
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kKVStages;
+      const uint32_t ph = (j / kKVStages) & 1;
+      mbar_wait(&k_full[st], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem_base + kTmemS, umma_desc_sw128(aq + k * 32, 1024, 16), umma_desc_sw128(ak + k * 32, 1024, 16),
+                  idesc_s, k ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+      mbar_wait(p_full, j & 1);      // P_j is in smem; S and the previous O_j have been read out of TMEM
+      mbar_wait(&v_full[st], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBKV / 16; ++k)
+          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
+                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, k ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (warps 0..3)
+    const int row = threadIdx.x;             // 0..127 == TMEM lane
+    const uint32_t lane_base = (uint32_t)(warp * 32);
+    float acc[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = smem_u32(sP) + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = min(kBKV, p.Lk - j * kBKV);  // columns of this tile that exist
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kBKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + c), v);
+        tmem_ld_wait();
+        if (c + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = ex2(m_run - m_new);  // first tile: ex2(-inf) = 0
+      m_run = m_new;
+      // fold in the previous tile's P V, then rescale
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c + i] = (acc[c + i] + __uint_as_float(v[i])) * alpha;
+        }
+      }
+      // pass 2: probabilities -> fp16 P tile in smem (the previous P V has completed: o_full was waited on)
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kBKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + c), v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          float e1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          if (c + i >= valid) e0 = 0.f;
+          if (c + i + 1 >= valid) e1 = 0.f;
+          // the row sum uses the fp16-rounded probabilities that the P V product actually sees
+          __half2 hh = __floats2half2_rn(e0, e1);
+          float2 back = __half22float2(hh);
+          rs += back.x + back.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        const uint32_t atom = p_row + (c >> 6) * (kBQ * 128);
+        const int u0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t addr = atom + (((u0 + q) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                       : "memory");
+        }
+      }
+      l_run = l_run * alpha + rs;
+      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core's async proxy
+      tc_fence_before();          // orders this thread's TMEM loads before the MMA that overwrites S / O
+      mbar_arrive(p_full);
+    }
+    // last P V
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int qrow = q0 + row;
+    __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl;
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), v);
+      tmem_ld_wait();
+      if (qrow < p.Lq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o4;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = c + 8 * q + 2 * i;
+            ow[i] = pack_half2((acc[e] + __uint_as_float(v[8 * q + 2 * i])) * inv_l,
+                               (acc[e + 1] + __uint_as_float(v[8 * q + 2 * i + 1])) * inv_l);
+          }
+          *reinterpret_cast<uint4*>(op + c + 8 * q) = o4;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
+                 int L) {
+  const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[4] = {2, (uint64_t)sl * 2, (uint64_t)sh * 2, (uint64_t)sb * 2};
+  const uint32_t box[4] = {(uint32_t)kD, 128, 1, 1};
+  return r3g_make_tmap_f16(ctx, m, base, 4, dims, strides, box);
+}
+
+}  // namespace
+
+extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* stream) {
+  if (!ctx || !ctx->encode_tiled)
+    return r3g_fail(ctx, R3G_E_CUDA, "attention: no CUDA device (there is no CPU fallback)");
+  if (!a || !a->q || !a->k || !a->v || !a->o) return r3g_fail(ctx, R3G_E_INVALID, "attention: null argument");
+  if (a->B < 1 || a->H < 1 || a->Lq < 1 || a->Lk < 1) return r3g_fail(ctx, R3G_E_INVALID, "attention: empty shape");
+  if (a->o_sl % 8 || a->o_sh % 8 || a->o_sb % 8 || ((uintptr_t)a->o) % 16)
+    return r3g_fail(ctx, R3G_E_INVALID, "attention: output strides must be multiples of 8 halfs");
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_qkv_map(ctx, &mq, a->q, a->q_sb, a->q_sh, a->q_sl, a->B, a->H, a->Lq))) return rc;
+  if ((rc = make_qkv_map(ctx, &mk, a->k, a->k_sb, a->k_sh, a->k_sl, a->B, a->H, a->Lk))) return rc;
+  if ((rc = make_qkv_map(ctx, &mv, a->v, a->v_sb, a->v_sh, a->v_sl, a->B, a->H, a->Lk))) return rc;
+  AttnParams p;
+  p.o = (__half*)a->o;
+  p.o_sb = a->o_sb; p.o_sh = a->o_sh; p.o_sl = a->o_sl;
+  p.Lq = a->Lq; p.Lk = a->Lk;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  dim3 grid((a->Lq + kBQ - 1) / kBQ, a->H, a->B);
+  attention_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}

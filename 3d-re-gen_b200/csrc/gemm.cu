@@ -1,0 +1,314 @@
+// r3g_linear: Y = epilogue(X . W^T + bias) on the 5th-gen tensor cores.
+//
+// Persistent, warp-specialised sm_100a kernel:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles of X and W into a smem ring)
+//   warp 1      MMA issuer     (one elected thread: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16;
+//                               fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps
+//                               the main loop of tile i+1)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: one accumulator row per thread; bias, GELU, gate*y+residual,
+//                               fp16/fp32 conversion, 16-byte global stores)
+// Covers every nn.Linear on the hot path: DiT qkv/proj/mlp/linear1/linear2 (hunyuan3ddit.py:196-216,259-267),
+// ShapeVAE c_qkv/c_proj/c_fc (attention_blocks.py:166-182,345-363), geo-decoder query_proj/c_q/c_kv/c_proj/mlp
+// (attention_blocks.py:250-261,484-494).
+#include <cuda_fp16.h>
+
+#include "r3g_internal.h"
+#include "r3g_ptx.cuh"
+
+namespace {
+
+using namespace r3g;
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 halfs = one 128-byte swizzle row
+constexpr int kNumThreads = 192;
+constexpr int kNumEpilogueWarps = 4;
+
+struct LinearParams {
+  int M, N, K;
+  const __half* bias;
+  void* y;
+  int64_t ldy;
+  int seg_len, seg_stride, seg_off;
+  int act, act_col0, act_col1;
+  const __half* gate;
+  int64_t gate_ld;
+  int gate_rows;
+  const __half* residual;
+  int out_f32;
+  int tiles_m, tiles_n;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageBytesA = BM * BK * 2;
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh through exp for fp32-level accuracy
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float e = __expf(2.f * u);
+  const float th = 1.f - __fdividef(2.f, e + 1.f);
+  return 0.5f * x * (1.f + th);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+              const LinearParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full_bar = empty_bar + C::kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kNumEpilogueWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kStageBytesA;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_2d(sa, &tmap_x, &full_bar[stage], kb * BK, tm * BM, kEvictFirst);
+          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN, kEvictLast);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kStageBytesA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 1024, 16);
+            const uint64_t db = umma_desc_sw128(sb + k * 32, 1024, 16);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int r = tm * BM + row_in_tile;  // source row
+      const bool row_ok = r < p.M;
+      int64_t out_row = r;
+      if (p.seg_len > 0) out_row = (int64_t)(r / p.seg_len) * p.seg_stride + p.seg_off + (r % p.seg_len);
+      const __half* gate_row = p.gate ? p.gate + (int64_t)(row_ok ? r / p.gate_rows : 0) * p.gate_ld : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = tn * BN + c0;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0), v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 b4 = __ldg(bp + q);
+              const __half2* h = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 t = __half22float2(h[j]);
+                f[q * 8 + 2 * j] += t.x;
+                f[q * 8 + 2 * j + 1] += t.y;
+              }
+            }
+          }
+          if (p.act && n0 < p.act_col1 && n0 + 32 > p.act_col0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              if (n >= p.act_col0 && n < p.act_col1) {
+                // the reference's Linear output is fp16 before the activation sees it
+                const float xh = __half2float(__float2half_rn(f[j]));
+                f[j] = (p.act == 1) ? gelu_tanh_f(xh) : gelu_erf_f(xh);
+              }
+            }
+          }
+          if (p.residual) {
+            const __half* rp = p.residual + out_row * p.ldy + n0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 r4 = *reinterpret_cast<const uint4*>(rp + 8 * q);
+              const __half2* h = reinterpret_cast<const __half2*>(&r4);
+              uint4 g4 = make_uint4(0, 0, 0, 0);
+              if (gate_row) g4 = __ldg(reinterpret_cast<const uint4*>(gate_row + n0) + q);
+              const __half2* gh = reinterpret_cast<const __half2*>(&g4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 rr = __half22float2(h[j]);
+                float y0 = __half2float(__float2half_rn(f[q * 8 + 2 * j]));
+                float y1 = __half2float(__float2half_rn(f[q * 8 + 2 * j + 1]));
+                if (gate_row) {
+                  float2 gg = __half22float2(gh[j]);
+                  y0 = __half2float(__float2half_rn(gg.x * y0));
+                  y1 = __half2float(__float2half_rn(gg.y * y1));
+                }
+                f[q * 8 + 2 * j] = rr.x + y0;
+                f[q * 8 + 2 * j + 1] = rr.y + y1;
+              }
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_row * p.ldy + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + out_row * p.ldy + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_half2(f[8 * q + 0], f[8 * q + 1]);
+              o.y = pack_half2(f[8 * q + 2], f[8 * q + 3]);
+              o.z = pack_half2(f[8 * q + 4], f[8 * q + 5]);
+              o.w = pack_half2(f[8 * q + 6], f[8 * q + 7]);
+              op[q] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap tx, tw;
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    const uint64_t strides[2] = {2, (uint64_t)a->ldx * 2};
+    const uint32_t box[2] = {BK, BM};
+    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t strides[2] = {2, (uint64_t)a->K * 2};
+    const uint32_t box[2] = {BK, BN};
+    int rc = r3g_make_tmap_f16(ctx, &tw, a->w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  LinearParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = (const __half*)a->bias;
+  p.y = a->y; p.ldy = a->ldy;
+  p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
+  p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
+  p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
+  p.residual = (const __half*)a->residual;
+  p.out_f32 = a->out_f32;
+  p.tiles_m = (a->M + BM - 1) / BM;
+  p.tiles_n = (a->N + BN - 1) / BN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  linear_kernel<BN><<<grid, kNumThreads, C::kSmemBytes, s>>>(tx, tw, p);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+}  // namespace
+
+extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) {
+  if (!ctx || !ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "linear: no CUDA device (there is no CPU fallback)");
+  if (!a || !a->x || !a->w || !a->y) return r3g_fail(ctx, R3G_E_INVALID, "linear: null argument");
+  if (a->M <= 0) return R3G_OK;
+  if (a->N % 32 || a->K % 8 || a->ldx % 8 || a->ldy % 8)
+    return r3g_fail(ctx, R3G_E_INVALID, "linear: need N %% 32 == 0, K %% 8 == 0, ldx/ldy %% 8 == 0 (N=%d K=%d)", a->N,
+                    a->K);
+  if (a->residual && a->out_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: residual with fp32 output unsupported");
+  if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
+  cudaStream_t s = (cudaStream_t)stream;
+  // tile width: widest tile that still gives every SM work
+  const int tiles_m = (a->M + BM - 1) / BM;
+  if (a->N >= 256 && (int64_t)tiles_m * ((a->N + 255) / 256) >= ctx->num_sms) return launch_linear<256>(ctx, a, s);
+  if (a->N >= 128) return launch_linear<128>(ctx, a, s);
+  return launch_linear<64>(ctx, a, s);
+}

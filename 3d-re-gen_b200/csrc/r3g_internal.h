@@ -1,0 +1,53 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of libr3g.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/r3g.h"
+
+typedef CUresult (*r3g_pfn_encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill);
+
+struct r3g_ctx {
+  int device;
+  int num_sms;
+  int64_t launches;
+  char err[1024];
+  r3g_pfn_encode_tiled encode_tiled;
+  // pinned host scratch for small device->host results (mc counts)
+  int64_t* pinned;
+};
+
+static inline int r3g_fail(r3g_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define R3G_CUDA_OK(ctx, expr)                                                                         \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return r3g_fail((ctx), R3G_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define R3G_LAUNCH_OK(ctx)                                                                             \
+  do {                                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                                               \
+    if (_e != cudaSuccess)                                                                             \
+      return r3g_fail((ctx), R3G_E_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    (ctx)->launches++;                                                                                 \
+  } while (0)
+
+// 2D..4D fp16 tensor map with 128B swizzle; dims/strides innermost first, strides in BYTES for dims >= 1.
+int r3g_make_tmap_f16(r3g_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);

@@ -1,0 +1,555 @@
+// Row-wise / element-wise operators around the tensor-core kernels: LayerNorm(+adaLN modulation), per-head
+// q/k normalisation, tiny-M GEMV, timestep embedding, CFG + Euler step, grid Fourier features,
+// ln_post + output projection, depth back-projection.  All are HBM-bound: 128-bit accesses, one pass.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "r3g_internal.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
+__device__ __forceinline__ float rnd_h(float x) { return __half2float(__float2half_rn(x)); }
+
+struct alignas(16) Half8 {
+  __half2 v[4];
+};
+__device__ __forceinline__ void unpack8(const Half8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Half8 pack8(const float* f) {
+  Half8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row (<= 2048 halfs) lives in registers between the statistics and the write.
+constexpr int kLnMaxChunks = 8;  // 8 chunks * 32 lanes * 8 halfs = 2048
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t ldx,
+                                                        __half* __restrict__ y, int64_t ldy, int rows, int width,
+                                                        float eps, const __half* __restrict__ w,
+                                                        const __half* __restrict__ b,
+                                                        const __half* __restrict__ scale,
+                                                        const __half* __restrict__ shift, int64_t mod_ld,
+                                                        int rows_per_batch) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = width >> 3;
+  float v[kLnMaxChunks][8];
+  float s = 0.f;
+  const Half8* xr = reinterpret_cast<const Half8*>(x + (int64_t)row * ldx);
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      Half8 p = xr[c];
+      unpack8(p, v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = v[j][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
+  const int bi = rows_per_batch > 0 ? row / rows_per_batch : 0;
+  Half8* yr = reinterpret_cast<Half8*>(y + (int64_t)row * ldy);
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      float o[8], wf[8], bf[8];
+      if (w) { unpack8(reinterpret_cast<const Half8*>(w)[c], wf); }
+      if (b) { unpack8(reinterpret_cast<const Half8*>(b)[c], bf); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = (v[j][i] - mean) * rstd;
+        if (w) t = t * wf[i];
+        if (b) t = t + bf[i];
+        o[i] = t;
+      }
+      if (scale) {
+        // reference: (1 + scale) * LN(x) + shift, every op rounded to fp16 (hunyuan3ddit.py:193)
+        float sc[8], sh[8];
+        unpack8(reinterpret_cast<const Half8*>(scale + (int64_t)bi * mod_ld)[c], sc);
+        unpack8(reinterpret_cast<const Half8*>(shift + (int64_t)bi * mod_ld)[c], sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rnd_h(rnd_h(1.f + sc[i]) * rnd_h(o[i])) + sh[i];
+      }
+      yr[c] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- q/k norm
+// 8 lanes per 64-wide head, 4 (row, head, q|k) groups per warp.
+__global__ void __launch_bounds__(256) qk_norm_kernel(__half* __restrict__ buf, int64_t ld, int64_t ngroups,
+                                                      int heads, int64_t q_off, int64_t k_off, int64_t head_stride,
+                                                      int mode, float eps, const __half* __restrict__ q_w,
+                                                      const __half* __restrict__ q_b, const __half* __restrict__ k_w,
+                                                      const __half* __restrict__ k_b, int nsel) {
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool active = grp < ngroups;
+  const int64_t g = active ? grp : 0;
+  const int sel = (int)(g % nsel);
+  const int64_t rh = g / nsel;
+  const int h = (int)(rh % heads);
+  const int64_t row = rh / heads;
+  __half* p = buf + row * ld + (sel ? k_off : q_off) + (int64_t)h * head_stride + sub * 8;
+  const __half* wv = sel ? k_w : q_w;
+  const __half* bv = sel ? k_b : q_b;
+  float f[8];
+  Half8 in = *reinterpret_cast<const Half8*>(p);
+  unpack8(in, f);
+  float o[8], wf[8];
+  unpack8(reinterpret_cast<const Half8*>(wv)[sub], wf);
+  if (mode == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i] * f[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float rrms = rsqrtf(s * (1.f / 64.f) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rnd_h(f[i] * rrms) * wf[i];  // (x*rrms).to(fp16) * scale
+  } else {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mean = s * (1.f / 64.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float d = f[i] - mean;
+      q += d * d;
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    const float rstd = rsqrtf(q * (1.f / 64.f) + eps);
+    float bf[8];
+    if (bv) unpack8(reinterpret_cast<const Half8*>(bv)[sub], bf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (f[i] - mean) * rstd * wf[i] + (bv ? bf[i] : 0.f);
+  }
+  if (active) *reinterpret_cast<Half8*>(p) = pack8(o);
+}
+
+// ------------------------------------------------------------------------------------------- GEMV (M <= 8)
+constexpr int kGemvMaxB = 8;
+__global__ void __launch_bounds__(256) gemv_kernel(const __half* __restrict__ w, const __half* __restrict__ bias,
+                                                   const __half* __restrict__ vec, int64_t vec_ld,
+                                                   __half* __restrict__ out, int64_t out_ld, int B, int N, int K,
+                                                   int silu_in, int silu_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float acc[kGemvMaxB];
+#pragma unroll
+  for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
+  const Half8* wr = reinterpret_cast<const Half8*>(w + (int64_t)n * K);
+  for (int c = lane; c < (K >> 3); c += 32) {
+    float wf[8];
+    unpack8(wr[c], wf);
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) {
+      if (b < B) {
+        float xf[8];
+        unpack8(reinterpret_cast<const Half8*>(vec + (int64_t)b * vec_ld)[c], xf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xv = xf[i];
+          if (silu_in) xv = rnd_h(xv / (1.f + expf(-xv)));
+          acc[b] += wf[i] * xv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kGemvMaxB; ++b) {
+    if (b < B) {
+      float r = warp_sum(acc[b]);
+      if (lane == 0) {
+        if (bias) r += h2f(bias[n]);
+        if (silu_out) {
+          r = rnd_h(r);
+          r = r / (1.f + expf(-r));
+        }
+        out[(int64_t)b * out_ld + n] = __float2half_rn(r);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- timestep embedding
+__global__ void timestep_embedding_kernel(const __half* __restrict__ t, __half* __restrict__ out, int B, int dim,
+                                          float time_factor, float max_period) {
+  const int half_dim = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half_dim) return;
+  const int b = i / half_dim, k = i % half_dim;
+  const float ts = rnd_h(time_factor * h2f(t[b]));  // `time_factor * t` is evaluated in t's dtype (fp16)
+  const float freq = expf(-logf(max_period) * (float)k / (float)half_dim);
+  const float arg = ts * freq;
+  out[(int64_t)b * dim + k] = __float2half_rn(cosf(arg));
+  out[(int64_t)b * dim + half_dim + k] = __float2half_rn(sinf(arg));
+  if ((dim & 1) && k == 0) out[(int64_t)b * dim + dim - 1] = __float2half_rn(0.f);
+}
+
+// ------------------------------------------------------------------------------------------- CFG + Euler
+__global__ void cfg_euler_kernel(__half* __restrict__ x, const __half* __restrict__ v, __half* __restrict__ x_dup,
+                                 int64_t n, float guidance, float dsigma) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vc = h2f(v[i]), vu = h2f(v[n + i]);
+  // noise_pred_uncond + g * (cond - uncond), each op rounded to fp16 (pipelines.py:753)
+  const float mix = rnd_h(vu + rnd_h(guidance * rnd_h(vc - vu)));
+  // (sigma_next - sigma) is a 0-dim fp32 tensor: the product takes the fp16 dtype of model_output,
+  // the sum is fp32 (schedulers.py:300-309)
+  const float step = rnd_h(dsigma * mix);
+  const __half r = __float2half_rn(h2f(x[i]) + step);
+  x[i] = r;
+  if (x_dup) {
+    x_dup[i] = r;
+    x_dup[n + i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- grid Fourier features
+struct GridParams {
+  double lo[3], step[3], hi[3];
+  int R;
+  int num_freqs;
+  int include_pi;
+};
+
+__global__ void __launch_bounds__(256) grid_fourier_kernel(__half* __restrict__ out, int64_t out_ld, int64_t start,
+                                                           int64_t count, GridParams gp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t p = start + i;
+  const int n = gp.R + 1;
+  int idx[3];
+  idx[2] = (int)(p % n);
+  idx[1] = (int)((p / n) % n);
+  idx[0] = (int)(p / ((int64_t)n * n));
+  __half* o = out + i * out_ld;
+  float xh[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // np.linspace(lo, hi, R+1, dtype=float32): float64 arange*step+lo, endpoint forced, then float32, then fp16
+    double c = (idx[d] == gp.R) ? gp.hi[d] : __dadd_rn(__dmul_rn((double)idx[d], gp.step[d]), gp.lo[d]);
+    xh[d] = rnd_h((float)c);
+    o[d] = __float2half_rn(xh[d]);
+  }
+  const int F = gp.num_freqs;
+  for (int d = 0; d < 3; ++d)
+    for (int k = 0; k < F; ++k) {
+      float f = (float)(1 << k);
+      if (gp.include_pi) f = rnd_h(f * 3.14159265358979323846f);
+      const float e = rnd_h(xh[d] * f);  // fp16 product (frequencies buffer is cast to fp16 with the module)
+      o[3 + d * F + k] = __float2half_rn(sinf(e));
+      o[3 + 3 * F + d * F + k] = __float2half_rn(cosf(e));
+    }
+  for (int c = 3 + 6 * F; c < out_ld; ++c) o[c] = __float2half_rn(0.f);
+}
+
+// ------------------------------------------------------------------------------------------- ln_post + output_proj
+__global__ void __launch_bounds__(256) lnpost_dot_kernel(const __half* __restrict__ x, int64_t ldx, int rows,
+                                                         int width, float eps, const __half* __restrict__ ln_w,
+                                                         const __half* __restrict__ ln_b,
+                                                         const __half* __restrict__ w_out,
+                                                         const __half* __restrict__ b_out, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = width >> 3;
+  float v[kLnMaxChunks][8];
+  float s = 0.f;
+  const Half8* xr = reinterpret_cast<const Half8*>(x + (int64_t)row * ldx);
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      unpack8(xr[c], v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = v[j][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      float wf[8], bf[8], of[8];
+      unpack8(reinterpret_cast<const Half8*>(ln_w)[c], wf);
+      unpack8(reinterpret_cast<const Half8*>(ln_b)[c], bf);
+      unpack8(reinterpret_cast<const Half8*>(w_out)[c], of);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += rnd_h((v[j][i] - mean) * rstd * wf[i] + bf[i]) * of[i];
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = rnd_h(acc + (b_out ? h2f(b_out[0]) : 0.f));
+}
+
+// ------------------------------------------------------------------------------------------- back-projection
+struct UnprojectFrame {
+  double r[9];  // cam-to-world rotation, row-major
+  double t[3];
+  float fu, fv, cu, cv;
+};
+constexpr int kMaxFrames = 32;  // 32 * 112 B of kernel parameters
+struct UnprojectParams {
+  UnprojectFrame f[kMaxFrames];
+};
+
+template <bool kF64>
+__global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict__ depth, void* __restrict__ out,
+                                                        int H, int W, int frame0,
+                                                        const __grid_constant__ UnprojectParams prm) {
+  // one thread = 2 horizontally adjacent pixels: 8-byte load, 3 x 16-byte (f64) stores
+  const int s = blockIdx.z;
+  const UnprojectFrame& fr = prm.f[s];
+  const int64_t pairs_per_frame = ((int64_t)H * W + 1) / 2;
+  const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= pairs_per_frame) return;
+  const int64_t frame_off = (int64_t)(frame0 + s) * H * W;
+  const int64_t p0 = 2 * pi;
+  float d[2];
+  const bool two = p0 + 1 < (int64_t)H * W;
+  const bool vec = two && (((frame_off + p0) & 1) == 0);  // 8/16-byte alignment of the pair
+  if (vec) {
+    float2 t = *reinterpret_cast<const float2*>(depth + frame_off + p0);
+    d[0] = t.x; d[1] = t.y;
+  } else {
+    d[0] = depth[frame_off + p0];
+    d[1] = two ? depth[frame_off + p0 + 1] : 0.f;
+  }
+  double wx[2], wy[2], wz[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int64_t p = p0 + k;
+    const int u = (int)(p % W), v = (int)(p / W);
+    // (u - cu) * depth / fu in float64, stored float32 (geometry.py:107-114)
+    const float xc = (float)(__ddiv_rn(__dmul_rn((double)u - (double)fr.cu, (double)d[k]), (double)fr.fu));
+    const float yc = (float)(__ddiv_rn(__dmul_rn((double)v - (double)fr.cv, (double)d[k]), (double)fr.fv));
+    const float zc = d[k];
+    // np.dot(cam, R^T) + t in float64 (geometry.py:80)
+    wx[k] = fma((double)zc, fr.r[2], fma((double)yc, fr.r[1], (double)xc * fr.r[0])) + fr.t[0];
+    wy[k] = fma((double)zc, fr.r[5], fma((double)yc, fr.r[4], (double)xc * fr.r[3])) + fr.t[1];
+    wz[k] = fma((double)zc, fr.r[8], fma((double)yc, fr.r[7], (double)xc * fr.r[6])) + fr.t[2];
+  }
+  if (kF64) {
+    double* o = reinterpret_cast<double*>(out) + 3 * (frame_off + p0);
+    if (vec) {
+      reinterpret_cast<double2*>(o)[0] = make_double2(wx[0], wy[0]);
+      reinterpret_cast<double2*>(o)[1] = make_double2(wz[0], wx[1]);
+      reinterpret_cast<double2*>(o)[2] = make_double2(wy[1], wz[1]);
+    } else {
+      o[0] = wx[0]; o[1] = wy[0]; o[2] = wz[0];
+      if (two) { o[3] = wx[1]; o[4] = wy[1]; o[5] = wz[1]; }
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(out) + 3 * (frame_off + p0);
+    if (vec) {
+      reinterpret_cast<float2*>(o)[0] = make_float2((float)wx[0], (float)wy[0]);
+      reinterpret_cast<float2*>(o)[1] = make_float2((float)wz[0], (float)wx[1]);
+      reinterpret_cast<float2*>(o)[2] = make_float2((float)wy[1], (float)wz[1]);
+    } else {
+      o[0] = (float)wx[0]; o[1] = (float)wy[0]; o[2] = (float)wz[0];
+      if (two) { o[3] = (float)wx[1]; o[4] = (float)wy[1]; o[5] = (float)wz[1]; }
+    }
+  }
+}
+
+}  // namespace
+
+#define R3G_NEED_GPU(ctx, name) \
+  if (!(ctx) || !(ctx)->encode_tiled) return r3g_fail((ctx), R3G_E_CUDA, name ": no CUDA device (there is no CPU fallback)")
+
+extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width,
+                             float eps, const void* w, const void* b, const void* scale, const void* shift,
+                             int64_t mod_ld, int rows_per_batch, void* stream) {
+  R3G_NEED_GPU(ctx, "layernorm");
+  if (width % 8 || width > kLnMaxChunks * 256 || ldx % 8 || ldy % 8 || (scale && (mod_ld % 8)))
+    return r3g_fail(ctx, R3G_E_INVALID, "layernorm: width %d must be a multiple of 8 and <= %d", width,
+                    kLnMaxChunks * 256);
+  if ((scale == nullptr) != (shift == nullptr)) return r3g_fail(ctx, R3G_E_INVALID, "layernorm: scale/shift pair");
+  if (rows <= 0) return R3G_OK;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, (__half*)y, ldy, rows, width, eps, (const __half*)w, (const __half*)b,
+      (const __half*)scale, (const __half*)shift, mod_ld, rows_per_batch);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int heads, int64_t q_off, int64_t k_off,
+                           int64_t head_stride, int mode, float eps, const void* q_w, const void* q_b,
+                           const void* k_w, const void* k_b, void* stream) {
+  R3G_NEED_GPU(ctx, "qk_norm");
+  if (ld % 8 || q_off % 8 || k_off % 8 || head_stride % 8 || !q_w)
+    return r3g_fail(ctx, R3G_E_INVALID, "qk_norm: offsets/strides must be multiples of 8 halfs");
+  const int nsel = k_w ? 2 : 1;
+  const int64_t ngroups = (int64_t)rows * heads * nsel;
+  if (ngroups <= 0) return R3G_OK;
+  const int64_t threads = ngroups * 8;
+  qk_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (__half*)buf, ld, ngroups, heads, q_off, k_off, head_stride, mode, eps, (const __half*)q_w,
+      (const __half*)q_b, (const __half*)k_w, (const __half*)k_b, nsel);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const void* vec, int64_t vec_ld, void* out,
+                        int64_t out_ld, int B, int N, int K, int silu_in, int silu_out, void* stream) {
+  R3G_NEED_GPU(ctx, "gemv");
+  if (B < 1 || B > kGemvMaxB || K % 8 || vec_ld % 8)
+    return r3g_fail(ctx, R3G_E_INVALID, "gemv: B in [1,%d], K %% 8 == 0 required", kGemvMaxB);
+  gemv_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)w, (const __half*)bias,
+                                                               (const __half*)vec, vec_ld, (__half*)out, out_ld, B, N,
+                                                               K, silu_in, silu_out);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_timestep_embedding(r3g_ctx* ctx, const void* t_f16, void* out, int B, int dim, float time_factor,
+                                      float max_period, void* stream) {
+  R3G_NEED_GPU(ctx, "timestep_embedding");
+  const int n = B * (dim / 2);
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const __half*)t_f16, (__half*)out, B,
+                                                                                 dim, time_factor, max_period);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_cfg_euler_step(r3g_ctx* ctx, void* x, const void* v, void* x_dup, int64_t n, float guidance,
+                                  float dsigma, void* stream) {
+  R3G_NEED_GPU(ctx, "cfg_euler_step");
+  cfg_euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, (const __half*)v,
+                                                                                    (__half*)x_dup, n, guidance,
+                                                                                    dsigma);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_grid_fourier(r3g_ctx* ctx, void* out, int64_t out_ld, int64_t start, int64_t count, int R,
+                                const float* bounds6_host, int num_freqs, int include_pi, void* stream) {
+  R3G_NEED_GPU(ctx, "grid_fourier");
+  if (!bounds6_host || R < 1 || out_ld < 3 + 6 * num_freqs)
+    return r3g_fail(ctx, R3G_E_INVALID, "grid_fourier: bad arguments");
+  GridParams gp;
+  for (int d = 0; d < 3; ++d) {
+    // bounds reach numpy as float64 (np.array of python floats, volume_decoders.py:159); the header
+    // passes them as the float32 the caller holds, widened here.
+    gp.lo[d] = (double)bounds6_host[d];
+    gp.hi[d] = (double)bounds6_host[3 + d];
+    gp.step[d] = (gp.hi[d] - gp.lo[d]) / (double)R;
+  }
+  gp.R = R;
+  gp.num_freqs = num_freqs;
+  gp.include_pi = include_pi;
+  if (count <= 0) return R3G_OK;
+  grid_fourier_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__half*)out, out_ld, start,
+                                                                                           count, gp);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width, float eps,
+                              const void* ln_w, const void* ln_b, const void* w_out, const void* b_out, float* out,
+                              void* stream) {
+  R3G_NEED_GPU(ctx, "lnpost_dot");
+  if (width % 8 || width > kLnMaxChunks * 256 || ldx % 8) return r3g_fail(ctx, R3G_E_INVALID, "lnpost_dot: width");
+  if (rows <= 0) return R3G_OK;
+  lnpost_dot_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, rows, width, eps,
+                                                                        (const __half*)ln_w, (const __half*)ln_b,
+                                                                        (const __half*)w_out, (const __half*)b_out,
+                                                                        out);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+// Host part of closed_form_inverse_se3 (geometry.py:120-169) done the numpy way: R^T and -(R^T t) in float32
+// (sequential multiply-add, no fma), then widened to float64 because they are written into np.eye(4).
+static void se3_inverse_f32(const float* e, UnprojectFrame& f) {
+  volatile float acc;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) f.r[3 * i + j] = (double)e[4 * j + i];
+    acc = 0.f;
+    for (int j = 0; j < 3; ++j) {
+      volatile float prod = e[4 * j + i] * e[4 * j + 3];
+      acc = acc + prod;
+    }
+    f.t[i] = (double)(-acc);
+  }
+}
+
+extern "C" int r3g_unproject(r3g_ctx* ctx, const float* depth, const float* extrinsic_host,
+                             const float* intrinsic_host, void* out, int S, int H, int W, int out_f64, void* stream) {
+  R3G_NEED_GPU(ctx, "unproject");
+  if (!depth || !extrinsic_host || !intrinsic_host || !out || S < 1 || H < 1 || W < 1)
+    return r3g_fail(ctx, R3G_E_INVALID, "unproject: bad arguments");
+  const int64_t pairs = ((int64_t)H * W + 1) / 2;
+  for (int s0 = 0; s0 < S; s0 += kMaxFrames) {
+    const int ns = (S - s0) < kMaxFrames ? (S - s0) : kMaxFrames;
+    UnprojectParams prm;
+    for (int s = 0; s < ns; ++s) {
+      const float* e = extrinsic_host + 12 * (s0 + s);
+      const float* k = intrinsic_host + 9 * (s0 + s);
+      if (k[1] != 0.f || k[3] != 0.f) return r3g_fail(ctx, R3G_E_INVALID, "Intrinsic matrix must have zero skew");
+      se3_inverse_f32(e, prm.f[s]);
+      prm.f[s].fu = k[0]; prm.f[s].fv = k[4]; prm.f[s].cu = k[2]; prm.f[s].cv = k[5];
+    }
+    dim3 grid((unsigned)((pairs + 255) / 256), 1, ns);
+    if (out_f64)
+      unproject_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(depth, out, H, W, s0, prm);
+    else
+      unproject_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(depth, out, H, W, s0, prm);
+    R3G_LAUNCH_OK(ctx);
+  }
+  return R3G_OK;
+}

@@ -1,0 +1,235 @@
+"""Torch-tensor front end of the C ABI (include/r3g.h).  Torch is plumbing only: it owns device memory
+and the stream; every computation below happens in libr3g.so.  No fallback paths."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+
+
+def _ctx(t):
+    if not t.is_cuda:
+        raise RuntimeError("r3g ops need CUDA tensors: there is no CPU fallback")
+    return _abi.get_context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f16(t, name):
+    if t.dtype != torch.float16:
+        raise TypeError(f"{name} must be float16, got {t.dtype}")
+    return t
+
+
+def _rows(t, name):
+    """View an activation as [rows, width] with a unit inner stride; returns (tensor, rows, width, ld)."""
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name}: innermost stride must be 1")
+    w = t.shape[-1]
+    if t.dim() == 1:
+        return t, 1, w, w
+    t2 = t.reshape(-1, w) if t.is_contiguous() else t
+    if t2.dim() != 2:
+        raise ValueError(f"{name}: cannot view as 2-D without a copy")
+    return t2, t2.shape[0], w, t2.stride(0)
+
+
+def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
+           seg=None, out_dtype=torch.float16):
+    """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
+
+    x: [..., K] (rows may be strided), w: [N, K] contiguous, out: [..., N] (optional, may be a strided view).
+    seg=(seg_len, seg_stride, seg_off) remaps output rows; gate: [B, N] view with unit inner stride.
+    """
+    _f16(x, "x"); _f16(w, "w")
+    ctx = _ctx(x)
+    x2, M, K, ldx = _rows(x, "x")
+    N = w.shape[0]
+    if w.shape[1] != K or not w.is_contiguous():
+        raise ValueError("w must be contiguous [N, K]")
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=out_dtype)
+    o2, _, No, ldy = _rows(out, "out")
+    if No != N and seg is None and out.shape[-1] != N:
+        raise ValueError("out has the wrong width")
+    a = _abi.LinearArgs()
+    a.x, a.ldx, a.w, a.bias = x2.data_ptr(), ldx, w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    a.y, a.ldy = o2.data_ptr(), ldy
+    a.M, a.N, a.K = M, N, K
+    if seg is not None:
+        a.seg_len, a.seg_stride, a.seg_off = seg
+    a.act = act
+    a.act_col0, a.act_col1 = act_cols if act_cols is not None else (0, N)
+    if gate is not None:
+        _f16(gate, "gate")
+        a.gate, a.gate_ld, a.gate_rows = gate.data_ptr(), gate.stride(0), gate_rows
+    if residual is not None:
+        _f16(residual, "residual")
+        r2, _, _, ldr = _rows(residual, "residual")
+        if ldr != ldy:
+            raise ValueError("residual must share out's row stride")
+        a.residual = r2.data_ptr()
+    a.out_f32 = 1 if out.dtype == torch.float32 else 0
+    ctx.check(ctx.lib.r3g_linear(ctx.handle, C.byref(a), _stream()))
+    return out
+
+
+def attention(q, k, v, out=None, scale=None):
+    """softmax(q k^T * scale) v.  q: [B, Lq, H, 64] views (any strides with unit inner stride), k/v: [B, Lk, H, 64].
+    Returns/writes out: [B, Lq, H, 64] ("B L (H D)" when contiguous)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _f16(t, n)
+        if t.dim() != 4 or t.shape[-1] != 64 or t.stride(-1) != 1:
+            raise ValueError(f"{n} must be [B, L, H, 64] with unit inner stride")
+    ctx = _ctx(q)
+    B, Lq, H, _ = q.shape
+    Lk = k.shape[1]
+    if out is None:
+        out = torch.empty(B, Lq, H, 64, device=q.device, dtype=torch.float16)
+    a = _abi.AttentionArgs()
+    a.q, a.q_sb, a.q_sl, a.q_sh = q.data_ptr(), q.stride(0), q.stride(1), q.stride(2)
+    a.k, a.k_sb, a.k_sl, a.k_sh = k.data_ptr(), k.stride(0), k.stride(1), k.stride(2)
+    a.v, a.v_sb, a.v_sl, a.v_sh = v.data_ptr(), v.stride(0), v.stride(1), v.stride(2)
+    a.o, a.o_sb, a.o_sl, a.o_sh = out.data_ptr(), out.stride(0), out.stride(1), out.stride(2)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.scale = float(scale if scale is not None else 64 ** -0.5)
+    ctx.check(ctx.lib.r3g_attention(ctx.handle, C.byref(a), _stream()))
+    return out
+
+
+def layernorm(x, weight=None, bias=None, eps=1e-6, scale=None, shift=None, rows_per_batch=0, out=None):
+    """LayerNorm over the last dim (+ optional (1+scale)*y+shift modulation with per-batch [B, width] vectors)."""
+    _f16(x, "x")
+    ctx = _ctx(x)
+    x2, rows, width, ldx = _rows(x, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    o2, _, _, ldy = _rows(out, "out")
+    mod_ld = scale.stride(0) if scale is not None else 0
+    ctx.check(ctx.lib.r3g_layernorm(ctx.handle, _p(x2), ldx, _p(o2), ldy, rows, width, float(eps), _p(weight),
+                                    _p(bias), _p(scale), _p(shift), mod_ld, int(rows_per_batch), _stream()))
+    return out
+
+
+def qk_norm_(buf, heads, q_off, k_off, head_stride, mode, eps, q_w, q_b=None, k_w=None, k_b=None):
+    """In-place per-head RMS (mode 0) / LayerNorm (mode 1) of q (and k) inside a packed [rows, ld] buffer."""
+    _f16(buf, "buf")
+    ctx = _ctx(buf)
+    b2, rows, _, ld = _rows(buf, "buf")
+    ctx.check(ctx.lib.r3g_qk_norm(ctx.handle, _p(b2), ld, rows, heads, q_off, k_off, head_stride, mode, float(eps),
+                                  _p(q_w), _p(q_b), _p(k_w), _p(k_b), _stream()))
+    return buf
+
+
+def gemv(w, bias, vec, silu_in=False, silu_out=False, out=None):
+    """out[b] = W . act(vec[b]) + bias for B <= 8 rows."""
+    _f16(w, "w"); _f16(vec, "vec")
+    ctx = _ctx(vec)
+    B, K = vec.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(B, N, device=vec.device, dtype=torch.float16)
+    ctx.check(ctx.lib.r3g_gemv(ctx.handle, _p(w), _p(bias), _p(vec), vec.stride(0), _p(out), out.stride(0), B, N, K,
+                               int(silu_in), int(silu_out), _stream()))
+    return out
+
+
+def timestep_embedding(t, dim=256, time_factor=1000.0, max_period=10000.0):
+    _f16(t, "t")
+    ctx = _ctx(t)
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float16)
+    ctx.check(ctx.lib.r3g_timestep_embedding(ctx.handle, _p(t), _p(out), t.shape[0], dim, float(time_factor),
+                                             float(max_period), _stream()))
+    return out
+
+
+def cfg_euler_step_(x, v, guidance, dsigma, x_dup=None):
+    """x <- x + dsigma * (v_uncond + g (v_cond - v_uncond)); v = cat(cond, uncond)."""
+    _f16(x, "x"); _f16(v, "v")
+    ctx = _ctx(x)
+    n = x.numel()
+    if v.numel() != 2 * n or not (x.is_contiguous() and v.is_contiguous()):
+        raise ValueError("v must hold cond and uncond predictions, contiguous")
+    ctx.check(ctx.lib.r3g_cfg_euler_step(ctx.handle, _p(x), _p(v), _p(x_dup), n, float(guidance), float(dsigma),
+                                         _stream()))
+    return x
+
+
+def grid_fourier(out, start, count, R, bounds6, num_freqs, include_pi):
+    ctx = _ctx(out)
+    b = (C.c_float * 6)(*[float(v) for v in bounds6])
+    ctx.check(ctx.lib.r3g_grid_fourier(ctx.handle, _p(out), out.stride(0), int(start), int(count), int(R),
+                                       C.cast(b, C.c_void_p), int(num_freqs), int(include_pi), _stream()))
+    return out
+
+
+def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
+    ctx = _ctx(x)
+    x2, rows, width, ldx = _rows(x, "x")
+    ctx.check(ctx.lib.r3g_lnpost_dot(ctx.handle, _p(x2), ldx, rows, width, float(eps), _p(ln_w), _p(ln_b), _p(w_out),
+                                     _p(b_out), _p(out), _stream()))
+    return out
+
+
+def unproject(depth, extrinsic, intrinsic, out_dtype=torch.float64):
+    """depth: CUDA float32 [S,H,W]; extrinsic [S,3,4] / intrinsic [S,3,3]: host numpy/torch float32."""
+    ctx = _ctx(depth)
+    S, H, W = depth.shape
+    e = np.ascontiguousarray(np.asarray(extrinsic, dtype=np.float32).reshape(S, 12))
+    k = np.ascontiguousarray(np.asarray(intrinsic, dtype=np.float32).reshape(S, 9))
+    out = torch.empty(S, H, W, 3, device=depth.device, dtype=out_dtype)
+    ctx.check(ctx.lib.r3g_unproject(ctx.handle, _p(depth.contiguous()), e.ctypes.data_as(C.c_void_p),
+                                    k.ctypes.data_as(C.c_void_p), _p(out), S, H, W,
+                                    1 if out_dtype == torch.float64 else 0, _stream()))
+    return out
+
+
+class MarchingCubesError(RuntimeError):
+    pass
+
+
+def marching_cubes(grid, level=0.0, bounds=None):
+    """grid: CUDA float32 [n0,n1,n2].  Returns (verts float32 [V,3], faces int32 [F,3]) CUDA tensors in
+    skimage's output convention.  Raises ValueError / RuntimeError like skimage.measure.marching_cubes."""
+    if grid.dtype != torch.float32 or grid.dim() != 3:
+        raise TypeError("grid must be float32 [n0,n1,n2]")
+    grid = grid.contiguous()
+    ctx = _ctx(grid)
+    n0, n1, n2 = grid.shape
+    ws_bytes = ctx.lib.r3g_mc_workspace_bytes(n0, n1, n2)
+    ws = torch.empty(ws_bytes, device=grid.device, dtype=torch.uint8)
+    nv, nf = C.c_int64(0), C.c_int64(0)
+    rc = ctx.lib.r3g_mc_count(ctx.handle, _p(grid), n0, n1, n2, float(level), _p(ws), ws_bytes, C.byref(nv),
+                              C.byref(nf), _stream())
+    if rc == _abi.R3G_E_LEVEL:
+        raise ValueError("Surface level must be within volume data range.")
+    if rc == _abi.R3G_E_NOSURFACE:
+        raise RuntimeError("No surface found at the given iso value.")
+    ctx.check(rc)
+    verts = torch.empty(nv.value, 3, device=grid.device, dtype=torch.float32)
+    faces = torch.empty(nf.value, 3, device=grid.device, dtype=torch.int32)
+    bptr = C.c_void_p(0)
+    if bounds is not None:
+        barr = (C.c_double * 6)(*[float(v) for v in bounds])
+        bptr = C.cast(barr, C.c_void_p)
+    ctx.check(ctx.lib.r3g_mc_extract(ctx.handle, _p(grid), n0, n1, n2, float(level), bptr, _p(ws), ws_bytes,
+                                     _p(verts), _p(faces), _stream()))
+    return verts, faces
+
+
+def mc_classify(grid, level=0.0):
+    grid = grid.contiguous()
+    ctx = _ctx(grid)
+    n0, n1, n2 = grid.shape
+    out = torch.empty((n0 - 1) * (n1 - 1) * (n2 - 1), device=grid.device, dtype=torch.uint8)
+    ctx.check(ctx.lib.r3g_mc_classify(ctx.handle, _p(grid), n0, n1, n2, float(level), _p(out), _stream()))
+    return out.view(n0 - 1, n1 - 1, n2 - 1)

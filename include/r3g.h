@@ -1,0 +1,172 @@
+/* r3g -- C ABI of the B200-native hot path of 3D-RE-GEN (stage 3: Hunyuan3D-2 shape generation,
+ * stage 4: VGGT back-projection).  The reference has no FFI of its own: its operator interface is the
+ * set of Python plug points listed in SURVEY.md section 8(b).  Every entry point below names the reference
+ * interface (file:line under /root/reference) it sits underneath; the Python mirror of those
+ * interfaces lives in 3d-re-gen_b200/r3g/ and calls this library through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - All pointers are DEVICE pointers on the context's device unless the name ends in _host.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless stated otherwise.
+ *   - Return value: 0 = OK, negative = error (R3G_E_*); r3g_last_error(ctx) gives the message.
+ *   - A context is bound to one device and is not thread-safe; distinct contexts are independent.
+ *   - There is no CPU fallback: without a CUDA device every compute call returns R3G_E_CUDA.
+ */
+#ifndef R3G_H
+#define R3G_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r3g_ctx r3g_ctx;
+
+enum {
+  R3G_OK = 0,
+  R3G_E_INVALID = -1,    /* bad argument / unsupported shape */
+  R3G_E_CUDA = -2,       /* CUDA runtime / driver error (message has the string) */
+  R3G_E_WORKSPACE = -3,  /* workspace too small */
+  R3G_E_LEVEL = -4,      /* mc: level outside [min,max] of the volume  (skimage ValueError) */
+  R3G_E_NOSURFACE = -5   /* mc: no vertices                              (skimage RuntimeError) */
+};
+
+int r3g_version(void);
+int r3g_create(int device, r3g_ctx** out);
+void r3g_destroy(r3g_ctx* ctx);
+const char* r3g_last_error(r3g_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t r3g_launch_count(r3g_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Marching cubes.  Replaces MCSurfaceExtractor.run -> skimage.measure.marching_cubes(grid.cpu().numpy(),
+ * mc_level, method="lewiner") and the bbox rescale
+ *   (Hunyuan3D-2/hy3dgen/shapegen/models/autoencoders/surface_extractors.py:67-76, :50-64).
+ * grid: float32 [n0][n1][n2] (C order; the reference's grid_logits[i] with n = octree_resolution+1).
+ * Two phases so the caller can allocate exact outputs:
+ *   r3g_mc_count   : classify + count; SYNCHRONISES `stream`; writes *nv_host, *nf_host.
+ *                    Returns R3G_E_LEVEL / R3G_E_NOSURFACE like skimage raises.
+ *   r3g_mc_extract : emits verts float32 [nv][3] in array-axis order and faces int32 [nf][3] in skimage's
+ *                    default (gradient_direction='descent') winding, i.e. BEFORE export_to_trimesh's flip
+ *                    (Hunyuan3D-2/hy3dgen/shapegen/pipelines.py:102).  If bounds_host != NULL (6 doubles:
+ *                    min xyz, max xyz) vertices are rescaled v / n_axis * (max-min) + min in float64 and
+ *                    stored float32, as surface_extractors.py:74-75,55 do.
+ * workspace: r3g_mc_workspace_bytes(n0,n1,n2) bytes of device memory, contents need not be initialised;
+ *            the same workspace must be passed to count and extract.
+ */
+size_t r3g_mc_workspace_bytes(int n0, int n1, int n2);
+int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level, void* workspace,
+                 size_t workspace_bytes, int64_t* nv_host, int64_t* nf_host, void* stream);
+int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level,
+                   const double* bounds_host, void* workspace, size_t workspace_bytes, float* verts,
+                   int32_t* faces, void* stream);
+/* Per-cell base case 0..14 (Lewiner's `cases[cubeindex][0]`), uint8 [(n0-1)*(n1-1)*(n2-1)]; parity probe. */
+int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level,
+                    unsigned char* case_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense-contraction building blocks (tcgen05 / TMEM / TMA).  Used by the DiT, ShapeVAE and geo-decoder
+ * mirrors; exported so that tests can check each against the oracle in isolation.
+ *
+ * r3g_linear:  Y = epilogue( X[M,K] . W[N,K]^T + bias )  -- nn.Linear semantics, fp16 in, fp32 accumulate.
+ *   X row-major with leading dimension ldx (halfs), W row-major [N,K] contiguous, Y leading dimension ldy.
+ *   Output row r of X is written to row  (r / seg_len) * seg_stride + seg_off + (r % seg_len)  of Y
+ *   (seg_len = 0 disables the remap); this is how the txt/img streams of DoubleStreamBlock are written
+ *   into one joint [B, Ltxt+Limg, ...] buffer (hunyuan3ddit.py:205-207).
+ *   act: 0 none, 1 tanh-GELU (hunyuan3ddit.py:63-69), 2 erf-GELU (attention_blocks.py:178); applied to
+ *        output columns [act_col0, act_col1) only.
+ *   gate/residual: if residual != NULL,  Y = residual + gate[b, n] * (acc + bias)  with b = r / gate_rows
+ *        (gate == NULL means gate 1; gate_ld is the stride between batches in halfs), covering the gated
+ *        residuals of hunyuan3ddit.py:212-216,267 and the plain residuals of attention_blocks.py:296-299.
+ *        residual uses Y's row mapping and may alias Y.
+ *   out_f32: 0 -> Y is fp16, 1 -> Y is float32.
+ */
+typedef struct {
+  const void* x; int64_t ldx;
+  const void* w;
+  const void* bias;          /* fp16 [N] or NULL */
+  void* y; int64_t ldy;
+  int M, N, K;
+  int seg_len, seg_stride, seg_off;
+  int act, act_col0, act_col1;
+  const void* gate; int64_t gate_ld; int gate_rows;
+  const void* residual;      /* fp16, same geometry as y */
+  int out_f32;
+} r3g_linear_args;
+int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream);
+
+/* r3g_attention: O = softmax(Q K^T * scale) V, no mask (F.scaled_dot_product_attention call sites:
+ * hunyuan3ddit.py:33-36, attention_blocks.py:328, attention_processors.py:29-32, vggt/layers/attention.py:61).
+ * head_dim is 64.  Q/K/V/O are addressed by strides in halfs: element (b, h, l, d) at
+ * base + b*stride_b + h*stride_h + l*stride_l + d.  O has the "B L (H D)" layout of hunyuan3ddit.py:35 when
+ * o_stride_l = H*64, o_stride_h = 64.  O may alias Q (each CTA reads its Q tile before writing it). */
+typedef struct {
+  const void* q; int64_t q_sb, q_sh, q_sl;
+  const void* k; int64_t k_sb, k_sh, k_sl;
+  const void* v; int64_t v_sb, v_sh, v_sl;
+  void* o; int64_t o_sb, o_sh, o_sl;
+  int B, H, Lq, Lk;
+  float scale;
+} r3g_attention_args;
+int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise / element-wise operators of the DiT and VAE blocks (fp16 storage, fp32 math).
+ */
+/* y[r,:] = LN(x[r,:]) * (w or 1) + (b or 0), then  * (1 + scale[bi,:]) + shift[bi,:]  with bi = r / rows_per_batch
+ * (scale/shift NULL -> skipped).  LayerNorm over `width` with eps; covers nn.LayerNorm(affine=False)+modulation
+ * (hunyuan3ddit.py:192-193,257) and affine LayerNorm (attention_blocks.py:296-299,425-433). */
+int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width, float eps,
+                  const void* w, const void* b, const void* scale, const void* shift, int64_t mod_ld,
+                  int rows_per_batch, void* stream);
+/* In-place per-head normalisation of q and k inside a packed projection output.
+ * Element (r, h, d) of q lives at buf + r*ld + q_off + h*head_stride + d (same for k with k_off).
+ * mode 0: RMSNorm over d with learned scale, computed in fp32, rounded to fp16, THEN multiplied by the fp16
+ *         scale (hunyuan3ddit.py:83-104).  mode 1: LayerNorm(eps) with weight and bias (attention_blocks.py:315-316,
+ *         vggt/layers/attention.py:44-45).  k_w == NULL skips k (geo-decoder query side). */
+int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int heads, int64_t q_off, int64_t k_off,
+                int64_t head_stride, int mode, float eps, const void* q_w, const void* q_b, const void* k_w,
+                const void* k_b, void* stream);
+/* out[b, :] = W[N,K] . silu?(vec[b, :]) + bias   (tiny-M GEMV: Modulation.lin hunyuan3ddit.py:146-147,
+ * MLPEmbedder hunyuan3ddit.py:79-80, LastLayer.adaLN_modulation :275).  fp16 in/out, fp32 accumulate. */
+int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const void* vec, int64_t vec_ld, void* out,
+             int64_t out_ld, int B, int N, int K, int silu_in, int silu_out, void* stream);
+/* timestep_embedding(t, 256, time_factor=1000): cat(cos, sin), fp16 out [B,256] (hunyuan3ddit.py:39-60). */
+int r3g_timestep_embedding(r3g_ctx* ctx, const void* t_f16, void* out, int B, int dim, float time_factor,
+                           float max_period, void* stream);
+/* Classifier-free-guidance mix + flow-matching Euler step (pipelines.py:751-756, schedulers.py:300-309):
+ *   v = v_uncond + g*(v_cond - v_uncond)  (fp16 arithmetic like the reference), x <- fp16(fp32(x) + dsigma*v).
+ * v holds [2*n] halfs (cond first, pipelines.py:752); x holds n halfs; x_dup (optional) receives x twice
+ * (the next step's cat([latents]*2), pipelines.py:744). */
+int r3g_cfg_euler_step(r3g_ctx* ctx, void* x, const void* v, void* x_dup, int64_t n, float guidance,
+                       float dsigma, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SDF decode helpers (VanillaVolumeDecoder + CrossAttentionDecoder, volume_decoders.py:141-182,
+ * attention_blocks.py:484-494).
+ */
+/* Fourier features of the dense grid points [start, start+count) of the (R+1)^3 grid, x slowest / z fastest
+ * (generate_dense_grid_points, volume_decoders.py:122-138): coordinates np.linspace(min,max,R+1) in float32,
+ * cast to fp16 (volume_decoders.py:168), embedded as cat(x, sin(x*f), cos(x*f)) with f = 2^k (* pi)
+ * (attention_blocks.py:113-131) in fp16 arithmetic, zero-padded to out_ld columns. */
+int r3g_grid_fourier(r3g_ctx* ctx, void* out, int64_t out_ld, int64_t start, int64_t count, int R,
+                     const float* bounds6_host, int num_freqs, int include_pi, void* stream);
+/* logits[r] = float(fp16( LN(x[r,:]; w,b,eps) . w_out + b_out ))  -- ln_post + output_proj
+ * (attention_blocks.py:491-493), written to the float32 grid at out[r]. */
+int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width, float eps, const void* ln_w,
+                   const void* ln_b, const void* w_out, const void* b_out, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Back-projection.  Replaces unproject_depth_map_to_point_map (vggt/vggt/utils/geometry.py:15-117):
+ * depth float32 [S,H,W] on the device (the reference squeezes a trailing 1); extrinsic float32 [S,3,4]
+ * (cam from world) and intrinsic float32 [S,3,3] are HOST arrays (they are numpy arrays at this point in
+ * the reference, minimal_demo_vggt.py:319-321) -- the SE(3) inverse is done on the host in float32 exactly
+ * as closed_form_inverse_se3 does (geometry.py:120-169).  out [S,H,W,3] float64 (out_f64=1, the
+ * reference's result dtype) or float32. */
+int r3g_unproject(r3g_ctx* ctx, const float* depth, const float* extrinsic_host, const float* intrinsic_host,
+                  void* out, int S, int H, int W, int out_f64, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""ORACLE -- test infrastructure only.
+
+Generates tests/golden/*.npz by running the REFERENCE's own Python modules (imported from
+/root/reference, see oracle/ref_import.py) on seeded inputs with seeded random weights.
+Run in the build container only:  python oracle/make_golden.py
+The reference ships no weights and no golden vectors of its own, so these
+fixtures are the pin: weights are the modules' default initialisation under torch.manual_seed,
+rounded through fp16 (what a GPU run holds) and evaluated in fp32 on the CPU.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_import  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+
+def fp16_round_(module):
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(p.half().float())
+        for b in module.buffers():
+            if b.is_floating_point():
+                b.copy_(b.half().float())
+
+
+def sd_np(module, prefix=""):
+    return {"w:" + prefix + k: v.detach().half().numpy() for k, v in module.state_dict().items()}
+
+
+def golden_dit():
+    m = ref_import.hunyuan_dit()
+    cfg = dict(in_channels=64, context_in_dim=96, hidden_size=128, num_heads=2, depth=2, depth_single_blocks=2,
+               axes_dim=[64])
+    torch.manual_seed(0)
+    model = m.Hunyuan3DDiT(**cfg).eval()
+    # the default init leaves the RMSNorm scales at 1 and modulation small; perturb so every term matters
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("norm.scale"):
+                p.copy_(1 + 0.25 * torch.randn_like(p))
+            if ".bias" in n:
+                p.copy_(0.1 * torch.randn_like(p))
+    fp16_round_(model)
+    B, L, Lc = 2, 40, 24
+    x = torch.randn(B, L, 64).half().float()
+    cond = torch.randn(B, Lc, 96).half().float()
+    t = torch.tensor([0.3469, 0.3469]).half().float()
+    taps = []
+    hooks = [blk.register_forward_hook(lambda mod, i, o: taps.append(
+        torch.cat((o[1], o[0]), 1) if isinstance(o, tuple) else o)) for blk in
+        list(model.double_blocks) + list(model.single_blocks)]
+    with torch.no_grad():
+        y = model(x, t, {"main": cond})
+    for h in hooks:
+        h.remove()
+    d = sd_np(model)
+    d.update(x=x.numpy(), t=t.numpy(), cond=cond.numpy(), y=y.numpy(), cfg_heads=np.int64(2), cfg_depth=np.int64(2),
+             cfg_depth_single=np.int64(2))
+    for i, tp in enumerate(taps):
+        d[f"tap{i}"] = tp.numpy()
+    # timestep embedding in fp16, exactly as the GPU pipeline calls it (pipelines.py:747-749)
+    t16 = torch.tensor([0.0, 0.0204, 0.5102, 1.0], dtype=torch.float16)
+    d["temb_t"] = t16.numpy()
+    d["temb_out"] = m.timestep_embedding(t16, 256, 1000.0).numpy()  # positional, like hunyuan3ddit.py:390
+    np.savez_compressed(os.path.join(OUT, "dit_mini.npz"), **d)
+    print("dit_mini: y", tuple(y.shape), "taps", len(taps))
+
+
+def golden_vae():
+    ab, ap, vd = ref_import.hunyuan_autoencoders()
+    width, heads, layers, n_lat, embed = 128, 2, 2, 48, 64
+    torch.manual_seed(1)
+    fe = ab.FourierEmbedder(num_freqs=8, include_pi=False)
+    post_kl = torch.nn.Linear(embed, width)
+    tr = ab.Transformer(n_ctx=n_lat, width=width, layers=layers, heads=heads, qkv_bias=False, qk_norm=True)
+    geo = ab.CrossAttentionDecoder(fourier_embedder=fe, out_channels=1, num_latents=n_lat, mlp_expand_ratio=4,
+                                   downsample_ratio=1, enable_ln_post=True, width=width, heads=heads,
+                                   qkv_bias=False, qk_norm=True, label_type="binary")
+    with torch.no_grad():
+        for mod in (tr, geo):
+            for n, p in mod.named_parameters():
+                if "norm" in n or "ln_" in n:
+                    p.copy_((1.0 if n.endswith("weight") else 0.0) + 0.2 * torch.randn_like(p))
+    for mod in (post_kl, tr, geo):
+        mod.eval()
+        fp16_round_(mod)
+    z = torch.randn(1, n_lat, embed).half().float()
+    taps = []
+    hooks = [blk.register_forward_hook(lambda mod, i, o: taps.append(o)) for blk in tr.resblocks]
+    with torch.no_grad():
+        lat = tr(post_kl(z))
+        # VanillaVolumeDecoder casts the queries to latents.dtype: run it in fp32 but with fp16-quantised
+        # coordinates, the values the fp16 pipeline sees (volume_decoders.py:168)
+        R = 8
+        xyz, grid_size, _ = vd.generate_dense_grid_points(np.array([-1.01] * 3), np.array([1.01] * 3), R, "ij")
+        q = torch.from_numpy(xyz).half().float().reshape(1, -1, 3)
+        logits = geo(queries=q, latents=lat)
+        grid = logits.view(1, *grid_size).float()
+        emb = fe(q)
+    for h in hooks:
+        h.remove()
+    d = {}
+    d.update(sd_np(post_kl, "post_kl."))
+    d.update(sd_np(tr, "transformer."))
+    d.update(sd_np(geo, "geo_decoder."))
+    d = {k: v for k, v in d.items() if "fourier_embedder" not in k}
+    d.update(z=z.numpy(), latents=lat.numpy(), grid=grid.numpy(), xyz=xyz.reshape(-1, 3), fourier=emb.numpy()[0],
+             cfg_heads=np.int64(heads), cfg_layers=np.int64(layers), cfg_R=np.int64(R))
+    for i, tp in enumerate(taps):
+        d[f"tap{i}"] = tp.numpy()
+    np.savez_compressed(os.path.join(OUT, "vae_mini.npz"), **d)
+    print("vae_mini: grid", tuple(grid.shape), "range", float(grid.min()), float(grid.max()))
+
+
+def golden_scheduler():
+    s = ref_import.hunyuan_scheduler()
+    sch = s.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000)
+    d = {}
+    for n in (1, 5, 50):
+        sch.set_timesteps(sigmas=np.linspace(0, 1, n))
+        d[f"timesteps_{n}"] = sch.timesteps.numpy()
+        d[f"sigmas_{n}"] = sch.sigmas.numpy()
+    # three Euler steps on an fp16 sample, the dtype flow of pipelines.py:755-756
+    torch.manual_seed(2)
+    sch.set_timesteps(sigmas=np.linspace(0, 1, 5))
+    x = torch.randn(1, 16, 64).half()
+    xs = [x.numpy()]
+    vs = []
+    for t in sch.timesteps[:3]:
+        v = torch.randn(1, 16, 64).half()
+        x = sch.step(v, t, x).prev_sample
+        vs.append(v.numpy())
+        xs.append(x.numpy())
+    d["euler_x"] = np.stack(xs)
+    d["euler_v"] = np.stack(vs)
+    np.savez_compressed(os.path.join(OUT, "scheduler.npz"), **d)
+    print("scheduler: ok", d["sigmas_5"])
+
+
+def golden_unproject():
+    ref_import.vggt_package()
+    from vggt.utils.geometry import unproject_depth_map_to_point_map
+    rng = np.random.default_rng(3)
+    S, H, W = 3, 13, 18
+    depth = (0.5 + rng.random((S, H, W, 1))).astype(np.float32)
+    depth[0, 0, 0, 0] = 0.0
+    ang = rng.normal(size=(S, 3))
+    E = np.zeros((S, 3, 4), np.float32)
+    for s in range(S):
+        a, b, c = ang[s]
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        E[s, :, :3] = (Rz @ Ry @ Rx).astype(np.float32)
+        E[s, :, 3] = rng.normal(size=3).astype(np.float32)
+    K = np.zeros((S, 3, 3), np.float32)
+    K[:, 0, 0] = 300 + 50 * rng.random(S)
+    K[:, 1, 1] = 310 + 50 * rng.random(S)
+    K[:, 0, 2] = W / 2
+    K[:, 1, 2] = H / 2
+    K[:, 2, 2] = 1
+    pts = unproject_depth_map_to_point_map(depth, E, K)
+    assert pts.dtype == np.float64
+    np.savez_compressed(os.path.join(OUT, "unproject.npz"), depth=depth, extrinsic=E, intrinsic=K, points=pts)
+    print("unproject:", pts.shape, pts.dtype)
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "reference checkout not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_dit()
+    golden_vae()
+    golden_scheduler()
+    golden_unproject()
