@@ -1,0 +1,97 @@
+"""GPU: the tcgen05 building blocks (r3g_linear, r3g_attention) against fp32 PyTorch on the same inputs.
+Tolerances: fp16 inputs, fp32 accumulation, fp16 output rounding -> |err| <= 2^-10 * |y| + accumulation noise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(y, ref, rel=2e-3, what=""):
+    err = (y.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= rel * scale + 1e-3, f"{what}: err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 384, 256), (1, 64, 64), (129, 128, 1024), (2740, 3072, 1024),
+                                   (8884, 1024, 5120), (77, 96, 72), (5000, 7168, 1024), (640, 64, 1024)])
+def test_linear_plain(M, N, K):
+    from r3g import ops
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+    b = torch.randn(N, device="cuda").half()
+    y = ops.linear(x, w, b)
+    _check(y, F.linear(x.float(), w.float(), b.float()), what=f"{M}x{N}x{K}")
+    y32 = ops.linear(x, w, None, out_dtype=torch.float32)
+    _check(y32, F.linear(x.float(), w.float()), rel=1e-4, what="fp32 out")
+
+
+def test_linear_epilogues():
+    from r3g import ops
+    torch.manual_seed(5)
+    B, L, K, N = 2, 333, 256, 512
+    x = torch.randn(B * L, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") / 16).half()
+    b = (torch.randn(N, device="cuda") * 0.1).half()
+    lin = F.linear(x.float(), w.float(), b.float())
+    _check(ops.linear(x, w, b, act=ops.ACT_GELU_TANH), F.gelu(lin, approximate="tanh"), what="gelu tanh")
+    _check(ops.linear(x, w, b, act=ops.ACT_GELU_ERF), F.gelu(lin), what="gelu erf")
+    part = lin.clone(); part[:, 128:384] = F.gelu(lin[:, 128:384], approximate="tanh")
+    _check(ops.linear(x, w, b, act=ops.ACT_GELU_TANH, act_cols=(128, 384)), part, what="gelu on a column range")
+    res = torch.randn(B * L, N, device="cuda").half()
+    gate = torch.randn(B, N, device="cuda").half()
+    ref = res.float() + gate.float().repeat_interleave(L, 0) * lin
+    out = res.clone()
+    ops.linear(x, w, b, out=out, gate=gate, gate_rows=L, residual=out)
+    _check(out, ref, what="gated residual in place")
+    out2 = ops.linear(x, w, b, residual=res, out=torch.empty_like(res))
+    _check(out2, res.float() + lin, what="plain residual")
+    # row remap: two segments of L rows written into a joint [B, L+7, N] buffer at offset 7
+    joint = torch.zeros(B, L + 7, N, device="cuda", dtype=torch.float16)
+    ops.linear(x, w, b, out=joint.view(-1, N), seg=(L, L + 7, 7))
+    _check(joint[:, 7:].reshape(-1, N), lin, what="segment remap")
+    assert (joint[:, :7] == 0).all()
+    # strided input / output views
+    big = torch.randn(B * L, 1024, device="cuda").half()
+    obig = torch.zeros(B * L, 2048, device="cuda", dtype=torch.float16)
+    ops.linear(big[:, 512:768], w, b, out=obig[:, 1024:1536])
+    _check(obig[:, 1024:1536], F.linear(big[:, 512:768].float(), w.float(), b.float()), what="strided views")
+    assert (obig[:, :1024] == 0).all() and (obig[:, 1536:] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 1, 128, 128), (1, 2, 200, 300), (2, 16, 4442, 4442), (1, 16, 1000, 3072),
+                                       (2, 3, 1, 129), (1, 4, 257, 64)])
+def test_attention(B, H, Lq, Lk):
+    from r3g import ops
+    torch.manual_seed(Lq + Lk)
+    q = torch.randn(B, Lq, H, 64, device="cuda").half()
+    k = torch.randn(B, Lk, H, 64, device="cuda").half()
+    v = torch.randn(B, Lk, H, 64, device="cuda").half()
+    o = ops.attention(q, k, v)
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                         v.float().transpose(1, 2)).transpose(1, 2)
+    err = (o.float() - ref).abs().max().item()
+    assert err < 4e-3, f"attention err {err}"
+
+
+def test_attention_packed_qkv_in_place():
+    """q/k/v as strided views of one packed [B, L, 3, H, 64] buffer, output written over q (DiT layout)."""
+    from r3g import ops
+    torch.manual_seed(9)
+    B, L, H = 2, 700, 4
+    qkv = torch.randn(B, L, 3, H, 64, device="cuda").half()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                         v.float().transpose(1, 2)).transpose(1, 2)
+    kc, vc = k.clone(), v.clone()
+    ops.attention(q, k, v, out=q)
+    assert (q.float() - ref).abs().max().item() < 4e-3
+    assert torch.equal(k, kc) and torch.equal(v, vc)
+    # peaked softmax (large logits): running-max rescale path
+    q2 = (torch.randn(1, 300, 1, 64, device="cuda") * 6).half()
+    k2 = (torch.randn(1, 500, 1, 64, device="cuda") * 6).half()
+    v2 = torch.randn(1, 500, 1, 64, device="cuda").half()
+    ref2 = F.scaled_dot_product_attention(q2.float().transpose(1, 2), k2.float().transpose(1, 2),
+                                          v2.float().transpose(1, 2)).transpose(1, 2)
+    assert (ops.attention(q2, k2, v2).float() - ref2).abs().max().item() < 6e-3
