@@ -29,7 +29,9 @@ struct LinearParams {
   const __half* bias;
   void* y;
   int64_t ldy;
-  int seg_len, seg_stride, seg_off;
+  int seg_len;            // rows per segment (== M when unsegmented)
+  int64_t y_seg_stride;   // output rows between segment starts
+  int tiles_per_seg;
   int act, act_col0, act_col1;
   const __half* gate;
   int64_t gate_ld;
@@ -103,12 +105,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int sg = tm / p.tiles_per_seg, l0 = (tm % p.tiles_per_seg) * BM;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kStageBytesA;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_2d(sa, &tmap_x, &full_bar[stage], kb * BK, tm * BM, kEvictFirst);
+          tma_load_3d(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
           tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN, kEvictLast);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -156,10 +159,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int r = tm * BM + row_in_tile;  // source row
-      const bool row_ok = r < p.M;
-      int64_t out_row = r;
-      if (p.seg_len > 0) out_row = (int64_t)(r / p.seg_len) * p.seg_stride + p.seg_off + (r % p.seg_len);
+      const int sg = tm / p.tiles_per_seg;
+      const int l = (tm % p.tiles_per_seg) * BM + row_in_tile;  // row inside the segment
+      const bool row_ok = l < p.seg_len;
+      const int r = sg * p.seg_len + l;                          // logical row
+      const int64_t out_row = (int64_t)sg * p.y_seg_stride + l;
       const __half* gate_row = p.gate ? p.gate + (int64_t)(row_ok ? r / p.gate_rows : 0) * p.gate_ld : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -256,11 +260,13 @@ template <int BN>
 int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   using C = Cfg<BN>;
   CUtensorMap tx, tw;
+  const int seg_len = a->seg_len > 0 ? a->seg_len : a->M;
+  const int nseg = a->M / seg_len;
   {
-    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
-    const uint64_t strides[2] = {2, (uint64_t)a->ldx * 2};
-    const uint32_t box[2] = {BK, BM};
-    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 2, dims, strides, box);
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)seg_len, (uint64_t)nseg};
+    const uint64_t strides[3] = {2, (uint64_t)a->ldx * 2, (uint64_t)(nseg > 1 ? a->x_seg_stride : seg_len) * a->ldx * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 3, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -274,12 +280,14 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.bias = (const __half*)a->bias;
   p.y = a->y; p.ldy = a->ldy;
-  p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
+  p.seg_len = seg_len;
+  p.y_seg_stride = nseg > 1 ? a->y_seg_stride : seg_len;
+  p.tiles_per_seg = (seg_len + BM - 1) / BM;
   p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
   p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
   p.residual = (const __half*)a->residual;
   p.out_f32 = a->out_f32;
-  p.tiles_m = (a->M + BM - 1) / BM;
+  p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = (a->N + BN - 1) / BN;
   static bool attr_set = false;
   if (!attr_set) {
@@ -303,11 +311,13 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
   if (a->N % 32 || a->K % 8 || a->ldx % 8 || a->ldy % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "linear: need N %% 32 == 0, K %% 8 == 0, ldx/ldy %% 8 == 0 (N=%d K=%d)", a->N,
                     a->K);
+  if (a->seg_len > 0 && a->M % a->seg_len) return r3g_fail(ctx, R3G_E_INVALID, "linear: M must be a multiple of seg_len");
   if (a->residual && a->out_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: residual with fp32 output unsupported");
   if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
   cudaStream_t s = (cudaStream_t)stream;
   // tile width: widest tile that still gives every SM work
-  const int tiles_m = (a->M + BM - 1) / BM;
+  const int seg_len_ = a->seg_len > 0 ? a->seg_len : a->M;
+  const int tiles_m = (a->M / seg_len_) * ((seg_len_ + BM - 1) / BM);
   if (a->N >= 256 && (int64_t)tiles_m * ((a->N + 255) / 256) >= ctx->num_sms) return launch_linear<256>(ctx, a, s);
   if (a->N >= 128) return launch_linear<128>(ctx, a, s);
   return launch_linear<64>(ctx, a, s);

@@ -44,14 +44,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const __half* __restrict__ b,
                                                         const __half* __restrict__ scale,
                                                         const __half* __restrict__ shift, int64_t mod_ld,
-                                                        int rows_per_batch) {
+                                                        int rows_per_batch, int seg_len, int64_t x_seg_stride,
+                                                        int64_t y_seg_stride) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nchunks = width >> 3;
   float v[kLnMaxChunks][8];
   float s = 0.f;
-  const Half8* xr = reinterpret_cast<const Half8*>(x + (int64_t)row * ldx);
+  int64_t xrow = row, yrow = row;
+  if (seg_len > 0) {
+    const int sg = row / seg_len, l = row - sg * seg_len;
+    xrow = sg * x_seg_stride + l;
+    yrow = sg * y_seg_stride + l;
+  }
+  const Half8* xr = reinterpret_cast<const Half8*>(x + xrow * ldx);
 #pragma unroll
   for (int j = 0; j < kLnMaxChunks; ++j) {
     const int c = lane + 32 * j;
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
   const int bi = rows_per_batch > 0 ? row / rows_per_batch : 0;
-  Half8* yr = reinterpret_cast<Half8*>(y + (int64_t)row * ldy);
+  Half8* yr = reinterpret_cast<Half8*>(y + yrow * ldy);
 #pragma unroll
   for (int j = 0; j < kLnMaxChunks; ++j) {
     const int c = lane + 32 * j;
@@ -111,7 +118,8 @@ __global__ void __launch_bounds__(256) qk_norm_kernel(__half* __restrict__ buf, 
                                                       int heads, int64_t q_off, int64_t k_off, int64_t head_stride,
                                                       int mode, float eps, const __half* __restrict__ q_w,
                                                       const __half* __restrict__ q_b, const __half* __restrict__ k_w,
-                                                      const __half* __restrict__ k_b, int nsel) {
+                                                      const __half* __restrict__ k_b, int nsel, int seg_len,
+                                                      int64_t seg_stride) {
   const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
   const bool active = grp < ngroups;
@@ -119,7 +127,8 @@ __global__ void __launch_bounds__(256) qk_norm_kernel(__half* __restrict__ buf, 
   const int sel = (int)(g % nsel);
   const int64_t rh = g / nsel;
   const int h = (int)(rh % heads);
-  const int64_t row = rh / heads;
+  int64_t row = rh / heads;
+  if (seg_len > 0) row = (row / seg_len) * seg_stride + (row % seg_len);
   __half* p = buf + row * ld + (sel ? k_off : q_off) + (int64_t)h * head_stride + sub * 8;
   const __half* wv = sel ? k_w : q_w;
   const __half* bv = sel ? k_b : q_b;
@@ -252,6 +261,8 @@ struct GridParams {
   int include_pi;
 };
 
+__device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi);
+
 __global__ void __launch_bounds__(256) grid_fourier_kernel(__half* __restrict__ out, int64_t out_ld, int64_t start,
                                                            int64_t count, GridParams gp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,9 +280,22 @@ __global__ void __launch_bounds__(256) grid_fourier_kernel(__half* __restrict__ 
     // np.linspace(lo, hi, R+1, dtype=float32): float64 arange*step+lo, endpoint forced, then float32, then fp16
     double c = (idx[d] == gp.R) ? gp.hi[d] : __dadd_rn(__dmul_rn((double)idx[d], gp.step[d]), gp.lo[d]);
     xh[d] = rnd_h((float)c);
-    o[d] = __float2half_rn(xh[d]);
   }
-  const int F = gp.num_freqs;
+  fourier_row(o, out_ld, xh, gp.num_freqs, gp.include_pi);
+}
+
+__global__ void __launch_bounds__(256) points_fourier_kernel(const __half* __restrict__ q, __half* __restrict__ out,
+                                                             int64_t out_ld, int64_t n, int F, int include_pi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xh[3] = {h2f(q[3 * i]), h2f(q[3 * i + 1]), h2f(q[3 * i + 2])};
+  fourier_row(out + i * out_ld, out_ld, xh, F, include_pi);
+}
+
+__device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) o[d] = __float2half_rn(xh[d]);
+  struct { int num_freqs; int include_pi; } gp = {F, include_pi};
   for (int d = 0; d < 3; ++d)
     for (int k = 0; k < F; ++k) {
       float f = (float)(1 << k);
@@ -413,7 +437,8 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
 
 extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width,
                              float eps, const void* w, const void* b, const void* scale, const void* shift,
-                             int64_t mod_ld, int rows_per_batch, void* stream) {
+                             int64_t mod_ld, int rows_per_batch, int seg_len, int64_t x_seg_stride,
+                             int64_t y_seg_stride, void* stream) {
   R3G_NEED_GPU(ctx, "layernorm");
   if (width % 8 || width > kLnMaxChunks * 256 || ldx % 8 || ldy % 8 || (scale && (mod_ld % 8)))
     return r3g_fail(ctx, R3G_E_INVALID, "layernorm: width %d must be a multiple of 8 and <= %d", width,
@@ -422,14 +447,14 @@ extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, 
   if (rows <= 0) return R3G_OK;
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ldx, (__half*)y, ldy, rows, width, eps, (const __half*)w, (const __half*)b,
-      (const __half*)scale, (const __half*)shift, mod_ld, rows_per_batch);
+      (const __half*)scale, (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride, y_seg_stride);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
 
 extern "C" int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int heads, int64_t q_off, int64_t k_off,
                            int64_t head_stride, int mode, float eps, const void* q_w, const void* q_b,
-                           const void* k_w, const void* k_b, void* stream) {
+                           const void* k_w, const void* k_b, int seg_len, int64_t seg_stride, void* stream) {
   R3G_NEED_GPU(ctx, "qk_norm");
   if (ld % 8 || q_off % 8 || k_off % 8 || head_stride % 8 || !q_w)
     return r3g_fail(ctx, R3G_E_INVALID, "qk_norm: offsets/strides must be multiples of 8 halfs");
@@ -439,7 +464,7 @@ extern "C" int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int he
   const int64_t threads = ngroups * 8;
   qk_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (__half*)buf, ld, ngroups, heads, q_off, k_off, head_stride, mode, eps, (const __half*)q_w,
-      (const __half*)q_b, (const __half*)k_w, (const __half*)k_b, nsel);
+      (const __half*)q_b, (const __half*)k_w, (const __half*)k_b, nsel, seg_len, seg_stride);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -495,6 +520,17 @@ extern "C" int r3g_grid_fourier(r3g_ctx* ctx, void* out, int64_t out_ld, int64_t
   if (count <= 0) return R3G_OK;
   grid_fourier_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__half*)out, out_ld, start,
                                                                                            count, gp);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_points_fourier(r3g_ctx* ctx, const void* queries, void* out, int64_t out_ld, int64_t n,
+                                  int num_freqs, int include_pi, void* stream) {
+  R3G_NEED_GPU(ctx, "points_fourier");
+  if (!queries || !out || out_ld < 3 + 6 * num_freqs) return r3g_fail(ctx, R3G_E_INVALID, "points_fourier: bad arguments");
+  if (n <= 0) return R3G_OK;
+  points_fourier_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)queries, (__half*)out, out_ld, n, num_freqs, include_pi);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

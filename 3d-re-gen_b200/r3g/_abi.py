@@ -21,7 +21,7 @@ class LinearArgs(C.Structure):
         ("bias", C.c_void_p),
         ("y", C.c_void_p), ("ldy", C.c_int64),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("seg_len", C.c_int), ("seg_stride", C.c_int), ("seg_off", C.c_int),
+        ("seg_len", C.c_int), ("x_seg_stride", C.c_int64), ("y_seg_stride", C.c_int64),
         ("act", C.c_int), ("act_col0", C.c_int), ("act_col1", C.c_int),
         ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("gate_rows", C.c_int),
         ("residual", C.c_void_p),
@@ -55,12 +55,13 @@ SIGNATURES = {
     "r3g_mc_classify": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "r3g_linear": (_i, [_vp, C.POINTER(LinearArgs), _vp]),
     "r3g_attention": (_i, [_vp, C.POINTER(AttentionArgs), _vp]),
-    "r3g_layernorm": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
-    "r3g_qk_norm": (_i, [_vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "r3g_layernorm": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _vp]),
+    "r3g_qk_norm": (_i, [_vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "r3g_gemv": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "r3g_timestep_embedding": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp]),
     "r3g_cfg_euler_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _vp]),
     "r3g_grid_fourier": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i, _i, _vp]),
+    "r3g_points_fourier": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
     "r3g_lnpost_dot": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "r3g_unproject": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }

@@ -31,42 +31,66 @@ def _f16(t, name):
 
 
 def _rows(t, name):
-    """View an activation as [rows, width] with a unit inner stride; returns (tensor, rows, width, ld)."""
+    """Describe an activation as segmented rows.  Accepts [..., W] contiguous, a 2-D strided view [M, W], or a
+    3-D view [S, L, W] whose segments are `stride(0)` apart (e.g. X[:, Lt:, :] of a joint txt+img buffer).
+    Returns (data_ptr_tensor, rows, width, ld, seg_len, seg_stride_rows)."""
     if t.stride(-1) != 1:
         raise ValueError(f"{name}: innermost stride must be 1")
     w = t.shape[-1]
     if t.dim() == 1:
-        return t, 1, w, w
-    t2 = t.reshape(-1, w) if t.is_contiguous() else t
-    if t2.dim() != 2:
-        raise ValueError(f"{name}: cannot view as 2-D without a copy")
-    return t2, t2.shape[0], w, t2.stride(0)
+        return t, 1, w, w, 0, 0
+    if t.is_contiguous():
+        t2 = t.reshape(-1, w)
+        return t2, t2.shape[0], w, w, 0, 0
+    if t.dim() == 2:
+        return t, t.shape[0], w, t.stride(0), 0, 0
+    if t.dim() == 3:
+        S, L, _ = t.shape
+        ld = t.stride(1)
+        if S == 1:
+            return t, L, w, ld, 0, 0
+        if t.stride(0) % ld:
+            raise ValueError(f"{name}: segment stride must be a multiple of the row stride")
+        return t, S * L, w, ld, L, t.stride(0) // ld
+    raise ValueError(f"{name}: cannot describe as (segmented) rows without a copy")
+
+
+def _merge_seg(xs, ys, name):
+    """x and y must agree on the segmentation (or one of them is unsegmented)."""
+    (xl, xst, xrows), (yl, yst) = xs, ys
+    if xl == 0 and yl == 0:
+        return 0, 0, 0
+    L = xl or yl
+    if (xl and yl and xl != yl) or xrows % L:
+        raise ValueError(f"{name}: input and output segment lengths differ")
+    return L, (xst if xl else L), (yst if yl else L)
 
 
 def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
-           seg=None, out_dtype=torch.float16):
+           out_dtype=torch.float16):
     """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
 
-    x: [..., K] (rows may be strided), w: [N, K] contiguous, out: [..., N] (optional, may be a strided view).
-    seg=(seg_len, seg_stride, seg_off) remaps output rows; gate: [B, N] view with unit inner stride.
+    x: [..., K] or a strided [M, K] / [S, L, K] view, w: [N, K] contiguous, out: same row structure, width N.
+    gate: [B, N] view with unit inner stride, applied to logical rows b = r // gate_rows.
+    residual must be the same view geometry as out (and may be out itself).
     """
     _f16(x, "x"); _f16(w, "w")
     ctx = _ctx(x)
-    x2, M, K, ldx = _rows(x, "x")
+    x2, M, K, ldx, xl, xst = _rows(x, "x")
     N = w.shape[0]
     if w.shape[1] != K or not w.is_contiguous():
         raise ValueError("w must be contiguous [N, K]")
     if out is None:
         out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=out_dtype)
-    o2, _, No, ldy = _rows(out, "out")
-    if No != N and seg is None and out.shape[-1] != N:
-        raise ValueError("out has the wrong width")
+    o2, Mo, No, ldy, yl, yst = _rows(out, "out")
+    if No != N or Mo != M:
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {M} rows x {N}")
+    seg_len, xs, ys = _merge_seg((xl, xst, M), (yl, yst), "linear")
     a = _abi.LinearArgs()
     a.x, a.ldx, a.w, a.bias = x2.data_ptr(), ldx, w.data_ptr(), (bias.data_ptr() if bias is not None else None)
     a.y, a.ldy = o2.data_ptr(), ldy
     a.M, a.N, a.K = M, N, K
-    if seg is not None:
-        a.seg_len, a.seg_stride, a.seg_off = seg
+    a.seg_len, a.x_seg_stride, a.y_seg_stride = seg_len, xs, ys
     a.act = act
     a.act_col0, a.act_col1 = act_cols if act_cols is not None else (0, N)
     if gate is not None:
@@ -74,9 +98,9 @@ def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None,
         a.gate, a.gate_ld, a.gate_rows = gate.data_ptr(), gate.stride(0), gate_rows
     if residual is not None:
         _f16(residual, "residual")
-        r2, _, _, ldr = _rows(residual, "residual")
-        if ldr != ldy:
-            raise ValueError("residual must share out's row stride")
+        r2, _, _, ldr, rl, rst = _rows(residual, "residual")
+        if ldr != ldy or (rl, rst) != (yl, yst):
+            raise ValueError("residual must share out's geometry")
         a.residual = r2.data_ptr()
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     ctx.check(ctx.lib.r3g_linear(ctx.handle, C.byref(a), _stream()))
@@ -107,26 +131,32 @@ def attention(q, k, v, out=None, scale=None):
 
 
 def layernorm(x, weight=None, bias=None, eps=1e-6, scale=None, shift=None, rows_per_batch=0, out=None):
-    """LayerNorm over the last dim (+ optional (1+scale)*y+shift modulation with per-batch [B, width] vectors)."""
+    """LayerNorm over the last dim (+ optional (1+scale)*y+shift modulation with per-batch [B, width] vectors).
+    x / out may be segmented views (see _rows)."""
     _f16(x, "x")
     ctx = _ctx(x)
-    x2, rows, width, ldx = _rows(x, "x")
+    x2, rows, width, ldx, xl, xst = _rows(x, "x")
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
-    o2, _, _, ldy = _rows(out, "out")
+    o2, orow, _, ldy, yl, yst = _rows(out, "out")
+    if orow != rows:
+        raise ValueError("layernorm: out has a different number of rows")
+    seg_len, xs, ys = _merge_seg((xl, xst, rows), (yl, yst), "layernorm")
     mod_ld = scale.stride(0) if scale is not None else 0
     ctx.check(ctx.lib.r3g_layernorm(ctx.handle, _p(x2), ldx, _p(o2), ldy, rows, width, float(eps), _p(weight),
-                                    _p(bias), _p(scale), _p(shift), mod_ld, int(rows_per_batch), _stream()))
+                                    _p(bias), _p(scale), _p(shift), mod_ld, int(rows_per_batch), seg_len, xs, ys,
+                                    _stream()))
     return out
 
 
 def qk_norm_(buf, heads, q_off, k_off, head_stride, mode, eps, q_w, q_b=None, k_w=None, k_b=None):
-    """In-place per-head RMS (mode 0) / LayerNorm (mode 1) of q (and k) inside a packed [rows, ld] buffer."""
+    """In-place per-head RMS (mode 0) / LayerNorm (mode 1) of q (and k) inside a packed buffer of rows
+    ([rows, ld] or a segmented [S, L, ld] view)."""
     _f16(buf, "buf")
     ctx = _ctx(buf)
-    b2, rows, _, ld = _rows(buf, "buf")
+    b2, rows, _, ld, sl, sst = _rows(buf, "buf")
     ctx.check(ctx.lib.r3g_qk_norm(ctx.handle, _p(b2), ld, rows, heads, q_off, k_off, head_stride, mode, float(eps),
-                                  _p(q_w), _p(q_b), _p(k_w), _p(k_b), _stream()))
+                                  _p(q_w), _p(q_b), _p(k_w), _p(k_b), sl, sst, _stream()))
     return buf
 
 
@@ -143,10 +173,11 @@ def gemv(w, bias, vec, silu_in=False, silu_out=False, out=None):
     return out
 
 
-def timestep_embedding(t, dim=256, time_factor=1000.0, max_period=10000.0):
+def timestep_embedding(t, dim=256, time_factor=1000.0, max_period=10000.0, out=None):
     _f16(t, "t")
     ctx = _ctx(t)
-    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float16)
+    if out is None:
+        out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float16)
     ctx.check(ctx.lib.r3g_timestep_embedding(ctx.handle, _p(t), _p(out), t.shape[0], dim, float(time_factor),
                                              float(max_period), _stream()))
     return out
@@ -172,9 +203,19 @@ def grid_fourier(out, start, count, R, bounds6, num_freqs, include_pi):
     return out
 
 
+def points_fourier(queries, out, num_freqs, include_pi):
+    """Fourier features of explicit fp16 query points [n, 3] -> out [n, >= 3+6F] (zero padded)."""
+    _f16(queries, "queries")
+    ctx = _ctx(queries)
+    q = queries.contiguous()
+    ctx.check(ctx.lib.r3g_points_fourier(ctx.handle, _p(q), _p(out), out.stride(0), q.shape[0], int(num_freqs),
+                                         int(include_pi), _stream()))
+    return out
+
+
 def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
     ctx = _ctx(x)
-    x2, rows, width, ldx = _rows(x, "x")
+    x2, rows, width, ldx, _, _ = _rows(x, "x")
     ctx.check(ctx.lib.r3g_lnpost_dot(ctx.handle, _p(x2), ldx, rows, width, float(eps), _p(ln_w), _p(ln_b), _p(w_out),
                                      _p(b_out), _p(out), _stream()))
     return out

@@ -70,9 +70,11 @@ int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, flo
  *
  * r3g_linear:  Y = epilogue( X[M,K] . W[N,K]^T + bias )  -- nn.Linear semantics, fp16 in, fp32 accumulate.
  *   X row-major with leading dimension ldx (halfs), W row-major [N,K] contiguous, Y leading dimension ldy.
- *   Output row r of X is written to row  (r / seg_len) * seg_stride + seg_off + (r % seg_len)  of Y
- *   (seg_len = 0 disables the remap); this is how the txt/img streams of DoubleStreamBlock are written
- *   into one joint [B, Ltxt+Limg, ...] buffer (hunyuan3ddit.py:205-207).
+ *   Rows may be segmented: logical row r = s * seg_len + l (0 <= l < seg_len) is read from X row
+ *   s * x_seg_stride + l and written to Y row s * y_seg_stride + l (seg_len = 0: one segment of M rows).
+ *   This is how the txt / img streams of DoubleStreamBlock (one segment per batch element) live inside one
+ *   joint [B, Ltxt+Limg, ...] buffer without any torch.cat (hunyuan3ddit.py:205-211,396); the caller offsets
+ *   the x / y pointers to the first row of the stream.
  *   act: 0 none, 1 tanh-GELU (hunyuan3ddit.py:63-69), 2 erf-GELU (attention_blocks.py:178); applied to
  *        output columns [act_col0, act_col1) only.
  *   gate/residual: if residual != NULL,  Y = residual + gate[b, n] * (acc + bias)  with b = r / gate_rows
@@ -87,7 +89,7 @@ typedef struct {
   const void* bias;          /* fp16 [N] or NULL */
   void* y; int64_t ldy;
   int M, N, K;
-  int seg_len, seg_stride, seg_off;
+  int seg_len; int64_t x_seg_stride, y_seg_stride;
   int act, act_col0, act_col1;
   const void* gate; int64_t gate_ld; int gate_rows;
   const void* residual;      /* fp16, same geometry as y */
@@ -115,10 +117,11 @@ int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* stream);
  */
 /* y[r,:] = LN(x[r,:]) * (w or 1) + (b or 0), then  * (1 + scale[bi,:]) + shift[bi,:]  with bi = r / rows_per_batch
  * (scale/shift NULL -> skipped).  LayerNorm over `width` with eps; covers nn.LayerNorm(affine=False)+modulation
- * (hunyuan3ddit.py:192-193,257) and affine LayerNorm (attention_blocks.py:296-299,425-433). */
+ * (hunyuan3ddit.py:192-193,257) and affine LayerNorm (attention_blocks.py:296-299,425-433).
+ * Rows are segmented like r3g_linear's: r = s*seg_len + l lives at x row s*x_seg_stride + l, y row s*y_seg_stride + l. */
 int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width, float eps,
                   const void* w, const void* b, const void* scale, const void* shift, int64_t mod_ld,
-                  int rows_per_batch, void* stream);
+                  int rows_per_batch, int seg_len, int64_t x_seg_stride, int64_t y_seg_stride, void* stream);
 /* In-place per-head normalisation of q and k inside a packed projection output.
  * Element (r, h, d) of q lives at buf + r*ld + q_off + h*head_stride + d (same for k with k_off).
  * mode 0: RMSNorm over d with learned scale, computed in fp32, rounded to fp16, THEN multiplied by the fp16
@@ -126,7 +129,7 @@ int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy
  *         vggt/layers/attention.py:44-45).  k_w == NULL skips k (geo-decoder query side). */
 int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int heads, int64_t q_off, int64_t k_off,
                 int64_t head_stride, int mode, float eps, const void* q_w, const void* q_b, const void* k_w,
-                const void* k_b, void* stream);
+                const void* k_b, int seg_len, int64_t seg_stride, void* stream);
 /* out[b, :] = W[N,K] . silu?(vec[b, :]) + bias   (tiny-M GEMV: Modulation.lin hunyuan3ddit.py:146-147,
  * MLPEmbedder hunyuan3ddit.py:79-80, LastLayer.adaLN_modulation :275).  fp16 in/out, fp32 accumulate. */
 int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const void* vec, int64_t vec_ld, void* out,
@@ -151,6 +154,10 @@ int r3g_cfg_euler_step(r3g_ctx* ctx, void* x, const void* v, void* x_dup, int64_
  * (attention_blocks.py:113-131) in fp16 arithmetic, zero-padded to out_ld columns. */
 int r3g_grid_fourier(r3g_ctx* ctx, void* out, int64_t out_ld, int64_t start, int64_t count, int R,
                      const float* bounds6_host, int num_freqs, int include_pi, void* stream);
+/* Same embedding for explicit query points: queries fp16 [n,3] (the `queries=` argument of
+ * CrossAttentionDecoder.forward, attention_blocks.py:484-486). */
+int r3g_points_fourier(r3g_ctx* ctx, const void* queries, void* out, int64_t out_ld, int64_t n, int num_freqs,
+                       int include_pi, void* stream);
 /* logits[r] = float(fp16( LN(x[r,:]; w,b,eps) . w_out + b_out ))  -- ln_post + output_proj
  * (attention_blocks.py:491-493), written to the float32 grid at out[r]. */
 int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width, float eps, const void* ln_w,

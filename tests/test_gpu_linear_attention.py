@@ -47,11 +47,18 @@ def test_linear_epilogues():
     _check(out, ref, what="gated residual in place")
     out2 = ops.linear(x, w, b, residual=res, out=torch.empty_like(res))
     _check(out2, res.float() + lin, what="plain residual")
-    # row remap: two segments of L rows written into a joint [B, L+7, N] buffer at offset 7
+    # segmented rows: two segments of L rows written into a joint [B, L+7, N] buffer at row offset 7 ...
     joint = torch.zeros(B, L + 7, N, device="cuda", dtype=torch.float16)
-    ops.linear(x, w, b, out=joint.view(-1, N), seg=(L, L + 7, 7))
-    _check(joint[:, 7:].reshape(-1, N), lin, what="segment remap")
+    ops.linear(x, w, b, out=joint[:, 7:])
+    _check(joint[:, 7:].reshape(-1, N), lin, what="segmented output")
     assert (joint[:, :7] == 0).all()
+    # ... and read back from a segmented input view, with the gated residual indexed by segment
+    xin = torch.zeros(B, L + 5, K, device="cuda", dtype=torch.float16)
+    xin[:, 5:] = x.view(B, L, K)
+    xin[:, :5] = 77.0
+    out3 = res.clone().view(B, L, N)
+    ops.linear(xin[:, 5:], w, b, out=out3, gate=gate, gate_rows=L, residual=out3)
+    _check(out3.view(-1, N), ref, what="segmented input + gated residual")
     # strided input / output views
     big = torch.randn(B * L, 1024, device="cuda").half()
     obig = torch.zeros(B * L, 2048, device="cuda", dtype=torch.float16)
