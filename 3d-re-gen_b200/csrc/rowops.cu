@@ -549,35 +549,23 @@ extern "C" int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows
   return R3G_OK;
 }
 
-// Host part of closed_form_inverse_se3 (geometry.py:120-169) done the numpy way: R^T and -(R^T t) in float32
-// (sequential multiply-add, no fma), then widened to float64 because they are written into np.eye(4).
-static void se3_inverse_f32(const float* e, UnprojectFrame& f) {
-  volatile float acc;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) f.r[3 * i + j] = (double)e[4 * j + i];
-    acc = 0.f;
-    for (int j = 0; j < 3; ++j) {
-      volatile float prod = e[4 * j + i] * e[4 * j + 3];
-      acc = acc + prod;
-    }
-    f.t[i] = (double)(-acc);
-  }
-}
-
-extern "C" int r3g_unproject(r3g_ctx* ctx, const float* depth, const float* extrinsic_host,
+extern "C" int r3g_unproject(r3g_ctx* ctx, const float* depth, const double* cam_to_world_host,
                              const float* intrinsic_host, void* out, int S, int H, int W, int out_f64, void* stream) {
   R3G_NEED_GPU(ctx, "unproject");
-  if (!depth || !extrinsic_host || !intrinsic_host || !out || S < 1 || H < 1 || W < 1)
+  if (!depth || !cam_to_world_host || !intrinsic_host || !out || S < 1 || H < 1 || W < 1)
     return r3g_fail(ctx, R3G_E_INVALID, "unproject: bad arguments");
   const int64_t pairs = ((int64_t)H * W + 1) / 2;
   for (int s0 = 0; s0 < S; s0 += kMaxFrames) {
     const int ns = (S - s0) < kMaxFrames ? (S - s0) : kMaxFrames;
     UnprojectParams prm;
     for (int s = 0; s < ns; ++s) {
-      const float* e = extrinsic_host + 12 * (s0 + s);
+      const double* e = cam_to_world_host + 12 * (s0 + s);
       const float* k = intrinsic_host + 9 * (s0 + s);
       if (k[1] != 0.f || k[3] != 0.f) return r3g_fail(ctx, R3G_E_INVALID, "Intrinsic matrix must have zero skew");
-      se3_inverse_f32(e, prm.f[s]);
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) prm.f[s].r[3 * i + j] = e[4 * i + j];
+        prm.f[s].t[i] = e[4 * i + 3];
+      }
       prm.f[s].fu = k[0]; prm.f[s].fv = k[4]; prm.f[s].cu = k[2]; prm.f[s].cv = k[5];
     }
     dim3 grid((unsigned)((pairs + 255) / 256), 1, ns);

@@ -221,14 +221,26 @@ def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
     return out
 
 
+def closed_form_inverse_se3(se3):
+    """numpy branch of vggt/vggt/utils/geometry.py:120-169: [R t]^-1 = [R^T, -R^T t], written into np.eye(4)
+    (so the result is float64 holding float32-computed entries)."""
+    se3 = np.asarray(se3)
+    R, T = se3[:, :3, :3], se3[:, :3, 3:]
+    Rt = np.transpose(R, (0, 2, 1))
+    inv = np.tile(np.eye(4), (len(R), 1, 1))
+    inv[:, :3, :3] = Rt
+    inv[:, :3, 3:] = -np.matmul(Rt, T)
+    return inv
+
+
 def unproject(depth, extrinsic, intrinsic, out_dtype=torch.float64):
-    """depth: CUDA float32 [S,H,W]; extrinsic [S,3,4] / intrinsic [S,3,3]: host numpy/torch float32."""
+    """depth: CUDA float32 [S,H,W]; extrinsic [S,3,4] / intrinsic [S,3,3]: host numpy float32 (cam from world)."""
     ctx = _ctx(depth)
     S, H, W = depth.shape
-    e = np.ascontiguousarray(np.asarray(extrinsic, dtype=np.float32).reshape(S, 12))
+    c2w = np.ascontiguousarray(closed_form_inverse_se3(np.asarray(extrinsic))[:, :3, :].astype(np.float64))
     k = np.ascontiguousarray(np.asarray(intrinsic, dtype=np.float32).reshape(S, 9))
     out = torch.empty(S, H, W, 3, device=depth.device, dtype=out_dtype)
-    ctx.check(ctx.lib.r3g_unproject(ctx.handle, _p(depth.contiguous()), e.ctypes.data_as(C.c_void_p),
+    ctx.check(ctx.lib.r3g_unproject(ctx.handle, _p(depth.contiguous()), c2w.ctypes.data_as(C.c_void_p),
                                     k.ctypes.data_as(C.c_void_p), _p(out), S, H, W,
                                     1 if out_dtype == torch.float64 else 0, _stream()))
     return out

@@ -48,7 +48,6 @@ class CrossAttentionDecoder:
         self.count = 0
         self.chunk_queries = 65536
         self.w = None
-        self._kv_key = None
         self._ws = {}
 
     def load(self, sd, prefix="geo_decoder."):
@@ -78,9 +77,6 @@ class CrossAttentionDecoder:
     # K/V of the latents: projected ONCE per object (the reference re-projects them for every chunk,
     # attention_blocks.py:250-258 with kv_cache=False)
     def _project_kv(self, latents):
-        key = (latents.data_ptr(), latents._version, tuple(latents.shape))
-        if self._kv_key == key:
-            return self._kv
         w, W, nh = self.w, self.width, self.heads
         n_lat = latents.shape[1]
         lat_n = ops.layernorm(latents[0], w["ln_2.weight"], w["ln_2.bias"], eps=1e-6)
@@ -88,9 +84,7 @@ class CrossAttentionDecoder:
         if self.qk_norm:
             ops.qk_norm_(kv, nh, 0, 0, 128, 1, 1e-6, w["k_norm.weight"], w["k_norm.bias"])
         kv5 = kv.view(1, n_lat, nh, 2, 64)
-        self._kv = (kv, kv5[:, :, :, 0], kv5[:, :, :, 1])
-        self._kv_key = key
-        return self._kv
+        return kv, kv5[:, :, :, 0], kv5[:, :, :, 1]
 
     def _workspace(self, n):
         ws = self._ws.get(n)
@@ -101,10 +95,10 @@ class CrossAttentionDecoder:
             self._ws = {n: ws}  # keep one size
         return ws
 
-    def _decode(self, ws, n, latents, out_f32):
+    def _decode(self, ws, n, kv, out_f32):
         """ws['emb'][:n] holds the embedded queries; writes n fp16-rounded logits (as float32) to out_f32[:n]."""
         w, W, nh = self.w, self.width, self.heads
-        _, k, v = self._project_kv(latents)
+        _, k, v = kv
         emb, x, xn, q, h = (ws[k_][:n] for k_ in ("emb", "x", "xn", "q", "h"))
         ops.linear(emb, w["query_proj.weight"], w["query_proj.bias"], out=x)
         ops.layernorm(x, w["ln_1.weight"], w["ln_1.bias"], eps=1e-6, out=xn)
@@ -126,10 +120,11 @@ class CrossAttentionDecoder:
         flat = grid_out.view(-1)
         cq = min(self.chunk_queries, total)
         ws = self._workspace(cq)
+        kv = self._project_kv(latents)
         for s in range(0, total, cq):
             n = min(cq, total - s)
             ops.grid_fourier(ws["emb"][:n], s, n, R, bounds6, self.num_freqs, self.include_pi)
-            self._decode(ws, n, latents, flat[s:s + n])
+            self._decode(ws, n, kv, flat[s:s + n])
         self.count += total
         return grid_out
 
@@ -144,10 +139,11 @@ class CrossAttentionDecoder:
         cq = min(self.chunk_queries, n)
         ws = self._workspace(cq)
         q16 = queries[0].to(torch.float16)
+        kv = self._project_kv(latents)
         for s in range(0, n, cq):
             m = min(cq, n - s)
             ops.points_fourier(q16[s:s + m], ws["emb"][:m], self.num_freqs, self.include_pi)
-            self._decode(ws, m, latents, out[s:s + m])
+            self._decode(ws, m, kv, out[s:s + m])
         self.count += n
         return out.to(torch.float16).view(1, n, 1)
 

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- objects -> mesh per second on the B200 (BASELINE.json metric, configs[1]):
+one "step" = one synthetic 512x512 masked crop -> DINOv2 conditioner -> 50 CFG DiT steps -> ShapeVAE ->
+257^3 SDF decode -> marching cubes -> mesh.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+`value`  : objects/s, preprocessed image tensor already resident in HBM, mesh left on the device.
+`e2e`    : objects/s through the public pipeline call with HOST buffers: RGBA crop in pinned host memory ->
+           H2D -> ... -> mesh vertices/faces copied back to host memory, every step.
+Objects are independent (src/2d_to_3d_models/run.py:188-193 shards them over GPUs), so N GPUs run N x K
+objects with no data-path collective; the finished meshes are gathered to rank 0 over NCCL inside the timed
+region (scaling = weak).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "3d-re-gen_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "objects->mesh/sec (256^3 SDF, 50 DiT steps)"
+WORKLOAD = "single 512x512 masked crop -> Hunyuan3D-2 shape gen, 50 DiT steps, 256^3 SDF"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="r3g", choices=["r3g", "reference"])
+    ap.add_argument("--octree", type=int, default=256)
+    ap.add_argument("--dit-steps", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="warm-up + timed device-resident loop only (for ncu launch lists); prints no bench line")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"),
+                    source="MEASURED_PEAKS.json (sustained cuBLAS bf16; copy bandwidth)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synthetic_crop(seed, size=512):
+    """512x512 RGBA: uniform-noise RGB inside an elliptical alpha mask."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size]
+    mask = (((xx - size / 2) / (0.38 * size)) ** 2 + ((yy - size / 2) / (0.30 * size)) ** 2) <= 1.0
+    rgba = np.zeros((size, size, 4), np.uint8)
+    rgba[..., :3] = rng.integers(0, 256, (size, size, 3), dtype=np.uint8)
+    rgba[..., 3] = mask * 255
+    return Image.fromarray(rgba, "RGBA")
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle port) on the host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline
+    vals, det = [], None
+    for i in range(args.warmup + args.steps):
+        v, det = cpu_baseline.time_object_sample(args.octree, args.dit_steps, mc_grid=97, dit_reps=1, chunk_reps=1)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "octree_resolution": args.octree, "dit_steps": args.dit_steps,
+                       "note": "each step times a bounded sample of the workload and extrapolates linearly"},
+            "cpu_baseline": {"value": value, "unit": "objects/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": det["sample"]},
+            "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def instrumented_linear_roofline(pipe, cond, peak_tflops):
+    """Dominant kernel = linear_kernel (every nn.Linear of the DiT: 272 launches per forward).  One eager DiT
+    forward with a CUDA-event pair around every r3g_linear launch on the launching stream; algorithmic FLOPs =
+    2*M*N*K of each launch."""
+    import torch
+    from r3g import ops
+    recs = []
+    orig = ops.linear
+
+    def timed(x, w, bias=None, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig(x, w, bias, **kw)
+        b.record()
+        M = x.numel() // x.shape[-1]
+        recs.append((a, b, 2.0 * M * w.shape[0] * w.shape[1]))
+        return out
+
+    x = torch.randn(2, pipe.vae.latent_shape[0], pipe.vae.latent_shape[1], device="cuda").half()
+    t = torch.full((2,), 0.5, device="cuda", dtype=torch.float16)
+    pipe.model(x, t, cond)  # warm
+    ops.linear = timed
+    try:
+        pipe.model(x, t, cond)
+    finally:
+        ops.linear = orig
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+    fl = sum(f for _, _, f in recs)
+    achieved = fl / ms / 1e9
+    return {"bound": "tensor", "kernel": "linear_kernel<BN> (tcgen05 GEMM, gemm.cu)", "launches_timed": len(recs),
+            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "traffic": None, "avg_launch_ms": ms / len(recs), "flops_per_launch_avg": fl / len(recs)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from r3g import _abi
+    from r3g.pipelines import Hunyuan3DDiTFlowMatchingPipeline
+    from r3g.dist import gather_meshes
+
+    pk = peaks()
+    pipe = Hunyuan3DDiTFlowMatchingPipeline.from_random(seed=0, device=f"cuda:{local}")
+    pipe.vae.surface_extractor.keep_on_device = True
+    ctx = _abi.get_context(local)
+    R = args.octree
+    K, W = args.steps, args.warmup
+
+    # synthetic inputs: K+W distinct crops per rank, prepared once on the host (pinned) and on the device
+    crops = [synthetic_crop(1234567 + rank * 1000 + i) for i in range(K + W)]
+    host_in = [pipe.image_processor(c)["image"].pin_memory() for c in crops]
+    dev_in = [h.cuda(non_blocking=True) for h in host_in]
+
+    def run_object(img_dev, seed):
+        cond = pipe.encode_cond(img_dev, {}, True)
+        return pipe(cond=cond, generator=torch.manual_seed(seed), num_inference_steps=args.dit_steps,
+                    octree_resolution=R, num_chunks=16000, output_type="mesh")[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_loop(e2e):
+        h2d = d2h = 0
+        meshes = []
+        launches0 = ctx.launches + pipe.replayed_launches
+        barrier()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(W, W + K):
+            if e2e:
+                img = host_in[i].cuda(non_blocking=True)
+                h2d += host_in[i].numel() * host_in[i].element_size()
+            else:
+                img = dev_in[i]
+            m = run_object(img, 1234567 + i)
+            if e2e and m is not None and world == 1:
+                v, f = m.mesh_v.cpu(), m.mesh_f.cpu()
+                d2h += v.numel() * 4 + f.numel() * 4
+            meshes.append(m)
+        if world > 1:
+            got = gather_meshes([(m.mesh_v, m.mesh_f) for m in meshes if m is not None], to_host=e2e)
+            if e2e and rank == 0:
+                d2h += sum(v.numel() * 4 + f.numel() * 4 for v, f in got)
+        t_end.record()
+        barrier()
+        ms = t_start.elapsed_time(t_end)
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), h2d, d2h, (ctx.launches + pipe.replayed_launches - launches0), meshes
+
+    for i in range(W):  # warm-up (also captures the DiT CUDA graph)
+        run_object(dev_in[i], 1234567 + i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, _, _, launches, meshes = timed_loop(e2e=False)
+    clk = clocks.stop() if rank == 0 else None
+    stage = dict(pipe.timings)
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms / K, "stages_ms_last_object": stage}))
+        return
+    ms_e2e, h2d, d2h, _, _ = timed_loop(e2e=True)
+
+    value = world * K / (ms / 1000.0)
+    e2e_value = world * K / (ms_e2e / 1000.0)
+    if rank == 0:
+        cond = pipe.encode_cond(dev_in[0], {}, True)
+        roof = instrumented_linear_roofline(pipe, cond, pk["tflops"])
+        roof["peak_source"] = pk["source"]
+        # whole-step view: algorithmic FLOPs of one object over the measured step time
+        Li, Lt = pipe.vae.latent_shape[0], cond["main"].shape[1]
+        fl_obj = (2 * args.dit_steps * pipe.model.flops_per_sample(Li, Lt) + pipe.vae.flops_forward()
+                  + (R + 1) ** 3 * pipe.vae.geo_decoder.flops_per_query(Li))
+        m0 = meshes[0]
+        line = {
+            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic (seeded random weights of the Hunyuan3D-2 architecture; noise crops)",
+            "config": {"workload": WORKLOAD, "octree_resolution": R, "dit_steps": args.dit_steps, "guidance": 5.0,
+                       "objects_per_gpu": K, "l2": "working set (2.6 GB of weights + 68 MB grid per object) exceeds L2",
+                       "parallelism": f"objects sharded over {world} GPU(s), NCCL gather of meshes to rank 0"},
+            "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d // K,
+                    "d2h_bytes_per_step": d2h // K, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "stages_ms_last_object": stage,
+            "object": {"algorithmic_tflop": fl_obj / 1e12, "achieved_tflops_whole_step": fl_obj / 1e12 / (ms / K / 1e3),
+                       "frac_of_peak_whole_step": fl_obj / 1e12 / (ms / K / 1e3) / pk["tflops"],
+                       "mesh_vertices": int(m0.mesh_v.shape[0]) if m0 is not None else 0,
+                       "mesh_faces": int(m0.mesh_f.shape[0]) if m0 is not None else 0},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import cpu_baseline
+            v, det = cpu_baseline.time_object_sample(R, args.dit_steps)
+            line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": det["sample"], "sampled_cpu_seconds": det["sampled_cpu_seconds"],
+                                    "extrapolated_object_s": det["extrapolated_object_s"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -164,13 +164,13 @@ int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width
                    const void* ln_b, const void* w_out, const void* b_out, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Back-projection.  Replaces unproject_depth_map_to_point_map (vggt/vggt/utils/geometry.py:15-117):
- * depth float32 [S,H,W] on the device (the reference squeezes a trailing 1); extrinsic float32 [S,3,4]
- * (cam from world) and intrinsic float32 [S,3,3] are HOST arrays (they are numpy arrays at this point in
- * the reference, minimal_demo_vggt.py:319-321) -- the SE(3) inverse is done on the host in float32 exactly
- * as closed_form_inverse_se3 does (geometry.py:120-169).  out [S,H,W,3] float64 (out_f64=1, the
- * reference's result dtype) or float32. */
-int r3g_unproject(r3g_ctx* ctx, const float* depth, const float* extrinsic_host, const float* intrinsic_host,
+ * Back-projection.  Replaces the per-pixel work of unproject_depth_map_to_point_map
+ * (vggt/vggt/utils/geometry.py:15-117): depth float32 [S,H,W] on the device (the reference squeezes a trailing 1).
+ * cam_to_world_host: float64 [S,3,4] = rows 0..2 of closed_form_inverse_se3(extrinsic) (geometry.py:74-77) --
+ * the 3x4 inverse is S tiny matrices computed by the host mirror with numpy exactly as the reference does (its
+ * float32 matmul rounding is BLAS-dependent, so it is not re-derived here).  intrinsic_host float32 [S,3,3].
+ * out [S,H,W,3] float64 (out_f64=1, the reference's result dtype) or float32. */
+int r3g_unproject(r3g_ctx* ctx, const float* depth, const double* cam_to_world_host, const float* intrinsic_host,
                   void* out, int S, int H, int W, int out_f64, void* stream);
 
 #ifdef __cplusplus

@@ -142,12 +142,15 @@ def flow_euler_step(sample, model_output, sigma, sigma_next):
     return prev.to(model_output.dtype)
 
 
-def denoise_loop(sd, latents, cond2, heads, depth, depth_single, steps, guidance):
-    """pipelines.py:741-759 with classifier-free guidance; cond2 = cat(cond, uncond)."""
+def denoise_loop(sd, latents, cond2, heads, depth, depth_single, steps, guidance, t_dtype=None):
+    """pipelines.py:741-759 with classifier-free guidance; cond2 = cat(cond, uncond).
+    t_dtype=torch.float16 quantises the timestep the way the fp16 pipeline does (`t.to(latents.dtype) / 1000`,
+    pipelines.py:747-749) while the rest of the oracle stays fp32."""
     timesteps, sigmas = flow_euler_sigmas(steps)
     for i, t in enumerate(timesteps):
         x2 = torch.cat([latents] * 2)
-        ts = t.expand(x2.shape[0]).to(latents.dtype) / 1000
+        ts = t.expand(x2.shape[0]).to(t_dtype or latents.dtype) / 1000
+        ts = ts.to(latents.dtype).to(latents.device)
         v = dit_forward(sd, x2, ts, cond2, heads, depth, depth_single)
         vc, vu = v.chunk(2)
         v = vu + guidance * (vc - vu)

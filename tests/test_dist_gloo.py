@@ -1,0 +1,74 @@
+"""CPU, world_size 2 over gloo: the N > 1 path's host logic (object sharding + variable-length mesh gather)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from r3g.dist import gather_meshes, shard_indices
+    items = list(range(7))
+    mine = shard_indices(len(items))
+    meshes = []
+    for i in mine:  # mesh i has i+1 vertices and 2i+1 faces with recognisable content
+        g = torch.Generator().manual_seed(i)
+        meshes.append((torch.rand(i + 1, 3, generator=g), torch.randint(0, i + 1, (2 * i + 1, 3), generator=g,
+                                                                        dtype=torch.int32)))
+    got = gather_meshes(meshes)
+    if rank == 0:
+        q.put((mine, [(v.clone(), f.clone()) for v, f in got]))
+    else:
+        q.put((mine, len(got)))
+    # a rank with nothing to send must not deadlock the gather
+    got2 = gather_meshes(meshes if rank == 0 else [])
+    if rank == 0:
+        assert len(got2) == len(meshes)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    r0 = [r for r in res if isinstance(r[1], list)][0]
+    r1 = [r for r in res if not isinstance(r[1], list)][0]
+    assert r0[0] == [0, 2, 4, 6] and r1[0] == [1, 3, 5] and r1[1] == 0
+    order = [0, 2, 4, 6, 1, 3, 5]  # (rank, local index)
+    assert len(r0[1]) == 7
+    for i, (v, f) in zip(order, r0[1]):
+        g = torch.Generator().manual_seed(i)
+        ev = torch.rand(i + 1, 3, generator=g)
+        ef = torch.randint(0, i + 1, (2 * i + 1, 3), generator=g, dtype=torch.int32)
+        assert torch.equal(v, ev) and torch.equal(f, ef)
+
+
+def test_single_process_passthrough():
+    sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
+    from r3g.dist import gather_meshes, shard_indices
+    assert shard_indices(5, 1, 3) == [1, 4]
+    m = [(torch.rand(4, 3), torch.zeros(2, 3, dtype=torch.int32))]
+    assert gather_meshes(m)[0][0] is m[0][0]

@@ -94,11 +94,11 @@ def test_cfg_euler_step_matches_reference_dtype_flow(golden_dir):
     ops.cfg_euler_step_(xd, v.cuda(), g, float((sig1 - sig0).half()), x_dup=dup)
     assert torch.equal(xd.cpu(), ref), "CPU dtype flow (the oracle): must be bit-exact"
     assert torch.equal(dup[0], xd[0]) and torch.equal(dup[1], xd[0])
+    # what torch's own CUDA kernels do with the same expression (the reference's actual execution): equal to one of
+    # the two d_sigma roundings -- the pipeline uses the fp16-rounded one, which must be the matching one
     vcc, vuc = v.cuda().chunk(2)
     ref_cuda = R.flow_euler_step(x.cuda(), vuc + g * (vcc - vuc), sig0.cuda(), sig1.cuda())
-    xd = x.cuda().clone()
-    ops.cfg_euler_step_(xd, v.cuda(), g, float(sig1 - sig0))
-    assert torch.equal(xd, ref_cuda), "CUDA dtype flow (what the reference executes on a GPU): must be bit-exact"
+    assert torch.equal(xd, ref_cuda), "torch CUDA flow differs from the CPU flow: revisit the pipeline's d_sigma"
 
 
 def test_grid_fourier_against_reference_fixture(golden_dir):
