@@ -13,6 +13,7 @@
 // Lk = 3072), vggt/layers/attention.py:61.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "r3g_internal.h"
 #include "r3g_ptx.cuh"
@@ -47,7 +48,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+attention_kernel_v1(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
@@ -264,6 +265,283 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2: software-pipelined.  Differences from v1 above:
+//   * the whole S row (128 fp32) is pulled into registers in one go, the TMEM S buffer is released at once
+//     (s_free) so the MMA warp issues S_{j+1} = Q K_{j+1}^T BEFORE P_j V_j: the tensor pipe works on the next
+//     scores while this tile's softmax runs;
+//   * O accumulates in TMEM across tiles (tcgen05.mma accumulate); the running-max rescale is LAZY: rows are
+//     rescaled (TMEM load-multiply-store) only when the max grew by more than 2^8, so probabilities are bounded by
+//     256 (exact in the final normalisation, fp16-safe) and the common path never touches O;
+//   * exp2 on packed halves (ex2.approx.f16x2: two results per MUFU op, output already the fp16 P operand),
+//     3-input max, row sums accumulated as half2 partials and folded into fp32 every 32 columns;
+//   * setmaxnreg moves registers from the TMA/MMA warps to the softmax warps.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t d;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(x));
+  return d;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
+  const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
+  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kTileBytes;
+  uint8_t* sP = sV + kKVStages * kTileBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* v_full = k_full + kKVStages;
+  uint64_t* k_empty = v_full + kKVStages;
+  uint64_t* v_empty = k_empty + kKVStages;
+  uint64_t* s_full = v_empty + kKVStages;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_free + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + kBKV - 1) / kBKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        tma_load_4d(sV + st * kTileBytes, &tmap_v, &v_full[st], 0, j * kBKV, h, b, kEvictLast);
+      }
+    }
+  } else if (warp == 5) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);
+    const uint32_t aq = smem_u32(sQ);
+    auto issue_s = [&](int j) {
+      const int st = j % kKVStages;
+      mbar_wait(&k_full[st], (j / kKVStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ak = smem_u32(sK + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem_base + kTmemS, umma_desc_sw128(aq + k * 32, 1024, 16), umma_desc_sw128(ak + k * 32, 1024, 16),
+                  idesc_s, k ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(s_free, j & 1);  // S_j now lives in the softmax warps' registers
+        issue_s(j + 1);
+      }
+      const int st = j % kKVStages;
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[st], (j / kKVStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBKV / 16; ++k)
+          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
+                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    const int row = threadIdx.x;
+    const uint32_t lane_base = (uint32_t)(warp * 32);
+    float m_used = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = smem_u32(sP) + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = min(kBKV, p.Lk - j * kBKV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t s[kBKV];
+#pragma unroll
+      for (int c = 0; c < kBKV; c += 32) tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + c), &s[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      if (valid < kBKV) {
+#pragma unroll
+        for (int i = 0; i < kBKV; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kBKV; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      }
+      const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = m_new - m_used > kRescaleThreshold;
+        // P buffer and O accumulator are both free once P_{j-1} V_{j-1} has completed
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2(m_used - m_new) : 1.f;
+#pragma unroll
+          for (int c = 0; c < kD; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_used = m_new;
+        }
+      }
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < kBKV; c += 32) {
+        uint32_t pk[16];
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint32_t e0 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
+                                                  fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+          const uint32_t e1 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 2]), p.scale_log2, -m_used),
+                                                  fmaf(__uint_as_float(s[c + i + 3]), p.scale_log2, -m_used)));
+          const uint32_t e2 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 4]), p.scale_log2, -m_used),
+                                                  fmaf(__uint_as_float(s[c + i + 5]), p.scale_log2, -m_used)));
+          const uint32_t e3 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 6]), p.scale_log2, -m_used),
+                                                  fmaf(__uint_as_float(s[c + i + 7]), p.scale_log2, -m_used)));
+          pk[(i >> 1) + 0] = e0; pk[(i >> 1) + 1] = e1; pk[(i >> 1) + 2] = e2; pk[(i >> 1) + 3] = e3;
+          a0 = hadd2_u32(a0, e0); a1 = hadd2_u32(a1, e1); a2 = hadd2_u32(a2, e2); a3 = hadd2_u32(a3, e3);
+        }
+        const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&a0));
+        const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&a1));
+        const float2 f2 = __half22float2(*reinterpret_cast<__half2*>(&a2));
+        const float2 f3 = __half22float2(*reinterpret_cast<__half2*>(&a3));
+        rs += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        const uint32_t atom = p_row + (c >> 6) * (kBQ * 128);
+        const int u0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t addr = atom + (((u0 + q) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                       : "memory");
+        }
+      }
+      l_run += rs;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int qrow = q0 + row;
+    __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl;
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), v);
+      tmem_ld_wait();
+      if (qrow < p.Lq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o4;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ow[i] = pack_half2(__uint_as_float(v[8 * q + 2 * i]) * inv_l, __uint_as_float(v[8 * q + 2 * i + 1]) * inv_l);
+          *reinterpret_cast<uint4*>(op + c + 8 * q) = o4;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
                  int L) {
   const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)L, (uint64_t)H, (uint64_t)B};
@@ -292,13 +570,21 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
+  static bool use_v1 = false;
   if (!attr_set) {
+    const char* e = getenv("R3G_ATTN_V1");
+    use_v1 = e && e[0] == '1';
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->H, a->B);
-  attention_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  if (use_v1)
+    attention_kernel_v1<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  else
+    attention_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -53,24 +53,31 @@ __device__ __forceinline__ bool owns_edge(int e, int x, int y, int z) {
 }
 
 __device__ __forceinline__ void load_cell(const float* __restrict__ g, const McDims& d, int x, int y, int z,
-                                          float level, double* cv, float* raw) {
+                                          float* raw) {
   const float* p = g + ((int64_t)z * d.n1 + y) * d.n2 + x;
   const int64_t sy = d.n2, sz = (int64_t)d.n1 * d.n2;
   raw[0] = __ldg(p);            raw[1] = __ldg(p + 1);
   raw[3] = __ldg(p + sy);       raw[2] = __ldg(p + sy + 1);
   raw[4] = __ldg(p + sz);       raw[5] = __ldg(p + sz + 1);
   raw[7] = __ldg(p + sz + sy);  raw[6] = __ldg(p + sz + sy + 1);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) cv[i] = (double)raw[i] - (double)level;
 }
 
-__device__ __forceinline__ Cell eval_cell(const double* cv, int x, int y, int z) {
-  Cell c;
-  c.ci = 0;
+// (double)v - (double)level > 0  <=>  v > level for floats (the difference is exact in double), so the cube index
+// is computed in float and the double-precision work below only runs for the few cells the surface crosses.
+__device__ __forceinline__ int cube_index(const float* raw, float level) {
+  int ci = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) c.ci |= (cv[i] > 0.0) ? (1 << i) : 0;
+  for (int i = 0; i < 8; ++i) ci |= (raw[i] > level) ? (1 << i) : 0;
+  return ci;
+}
+
+__device__ __forceinline__ Cell eval_cell(const float* raw, float level, double* cv, int x, int y, int z) {
+  Cell c;
+  c.ci = cube_index(raw, level);
   c.til = 0; c.nt = 0; c.nv = 0;
   if (c.ci == 0 || c.ci == 255) return c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cv[i] = (double)raw[i] - (double)level;
   int sub = 0, j = 0;
   unsigned amb = r3g_mc_amb_faces[c.ci];
   for (int f = 0; f < 6; ++f)
@@ -144,7 +151,7 @@ __device__ __forceinline__ bool cell_coords(const McDims& d, int64_t cell, int& 
 // Pass 1: per-block (vertex, triangle) counts and the volume's min/max (for skimage's level check).
 __global__ void __launch_bounds__(kThreads) mc_count_kernel(const float* __restrict__ g, McDims d, float level,
                                                             unsigned* __restrict__ block_counts,
-                                                            unsigned* __restrict__ minmax) {
+                                                            float* __restrict__ block_minmax) {
   const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int x, y, z;
   unsigned nv = 0, nt = 0;
@@ -152,10 +159,10 @@ __global__ void __launch_bounds__(kThreads) mc_count_kernel(const float* __restr
   if (cell_coords(d, cell, x, y, z)) {
     double cv[8];
     float raw[8];
-    load_cell(g, d, x, y, z, level, cv, raw);
+    load_cell(g, d, x, y, z, raw);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { lo = fminf(lo, raw[i]); hi = fmaxf(hi, raw[i]); }
-    Cell c = eval_cell(cv, x, y, z);
+    Cell c = eval_cell(raw, level, cv, x, y, z);
     nv = c.nv; nt = c.nt;
   }
   unsigned ev, et, tv, tt;
@@ -165,28 +172,33 @@ __global__ void __launch_bounds__(kThreads) mc_count_kernel(const float* __restr
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&minmax[0], f2ord(lo));
-    atomicMax(&minmax[1], f2ord(hi));
-  }
+  __shared__ float slo[kThreads / 32], shi[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
   if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) { lo = fminf(lo, slo[i]); hi = fmaxf(hi, shi[i]); }
     block_counts[2 * blockIdx.x] = tv;
     block_counts[2 * blockIdx.x + 1] = tt;
+    block_minmax[2 * blockIdx.x] = lo;      // no same-address atomics: the scan kernel reduces these
+    block_minmax[2 * blockIdx.x + 1] = hi;
   }
 }
 
 // Pass 2: exclusive scan of the per-block counts (single block; the array has ncells/256 entries).
 __global__ void __launch_bounds__(1024) mc_scan_kernel(const unsigned* __restrict__ counts,
                                                        unsigned* __restrict__ offsets, int nblocks,
-                                                       const unsigned* __restrict__ minmax,
+                                                       const float* __restrict__ block_minmax,
                                                        int64_t* __restrict__ totals) {
   __shared__ unsigned long long sv[32], st[32];
   __shared__ unsigned long long carry_v, carry_t;
   if (threadIdx.x == 0) { carry_v = 0; carry_t = 0; }
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float lo = INFINITY, hi = -INFINITY;
   for (int base = 0; base < nblocks; base += 1024) {
     int i = base + threadIdx.x;
+    if (i < nblocks) { lo = fminf(lo, block_minmax[2 * i]); hi = fmaxf(hi, block_minmax[2 * i + 1]); }
     unsigned long long a = (i < nblocks) ? counts[2 * i] : 0, b = (i < nblocks) ? counts[2 * i + 1] : 0;
     unsigned long long ia = a, ib = b;
 #pragma unroll
@@ -206,11 +218,20 @@ __global__ void __launch_bounds__(1024) mc_scan_kernel(const unsigned* __restric
     if (threadIdx.x == 1023) { carry_v = offa + ia; carry_t = offb + ib; }
     __syncthreads();
   }
+  __shared__ float slo[32], shi[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { slo[w] = lo; shi[w] = hi; }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    for (int k = 1; k < 32; ++k) { lo = fminf(lo, slo[k]); hi = fmaxf(hi, shi[k]); }
     totals[0] = (int64_t)carry_v;
     totals[1] = (int64_t)carry_t;
-    totals[2] = (int64_t)minmax[0];
-    totals[3] = (int64_t)minmax[1];
+    totals[2] = (int64_t)f2ord(lo);
+    totals[3] = (int64_t)f2ord(hi);
   }
 }
 
@@ -229,8 +250,10 @@ struct Rescale {
 // Pass 3: every cell writes the vertices it owns, in first-use order of its tiling, and publishes their ids.
 __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __restrict__ g, McDims d, float level,
                                                              const unsigned* __restrict__ block_offsets,
+                                                             const unsigned* __restrict__ block_counts,
                                                              int32_t* __restrict__ vid, float* __restrict__ verts,
                                                              Rescale rs) {
+  if (block_counts[2 * blockIdx.x] == 0) return;  // nothing to emit in this block (the common case)
   const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int x = 0, y = 0, z = 0;
   double cv[8];
@@ -238,8 +261,8 @@ __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __rest
   const bool valid = cell_coords(d, cell, x, y, z);
   if (valid) {
     float raw[8];
-    load_cell(g, d, x, y, z, level, cv, raw);
-    c = eval_cell(cv, x, y, z);
+    load_cell(g, d, x, y, z, raw);
+    c = eval_cell(raw, level, cv, x, y, z);
   }
   unsigned ev, et, tv, tt;
   block_scan2(c.nv, c.nt, ev, et, tv, tt);
@@ -293,16 +316,18 @@ __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __rest
 // Pass 4: faces, in cell order then tiling order, looking vertex ids up by grid edge.
 __global__ void __launch_bounds__(kThreads) mc_face_kernel(const float* __restrict__ g, McDims d, float level,
                                                            const unsigned* __restrict__ block_offsets,
+                                                           const unsigned* __restrict__ block_counts,
                                                            const int32_t* __restrict__ vid,
                                                            int32_t* __restrict__ faces) {
+  if (block_counts[2 * blockIdx.x + 1] == 0) return;
   const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int x = 0, y = 0, z = 0;
   Cell c; c.ci = 0; c.til = 0; c.nt = 0; c.nv = 0;
   if (cell_coords(d, cell, x, y, z)) {
     double cv[8];
     float raw[8];
-    load_cell(g, d, x, y, z, level, cv, raw);
-    c = eval_cell(cv, x, y, z);
+    load_cell(g, d, x, y, z, raw);
+    c = eval_cell(raw, level, cv, x, y, z);
   }
   unsigned ev, et, tv, tt;
   block_scan2(c.nv, c.nt, ev, et, tv, tt);
@@ -317,20 +342,16 @@ __global__ void __launch_bounds__(kThreads) mc_case_kernel(const float* __restri
   const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int x, y, z;
   if (!cell_coords(d, cell, x, y, z)) return;
-  double cv[8];
   float raw[8];
-  load_cell(g, d, x, y, z, level, cv, raw);
-  int ci = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ci |= (cv[i] > 0.0) ? (1 << i) : 0;
-  out[cell] = r3g_mc_case[ci];
+  load_cell(g, d, x, y, z, raw);
+  out[cell] = r3g_mc_case[cube_index(raw, level)];
 }
 
 struct McWorkspace {
   int32_t* vid;
   unsigned* counts;
   unsigned* offsets;
-  unsigned* minmax;
+  float* minmax;
   int64_t* totals;
   int nblocks;
 };
@@ -354,7 +375,7 @@ int carve(r3g_ctx* ctx, const McDims& d, void* ws, size_t ws_bytes, McWorkspace&
   w.vid = (int32_t*)(base + off);       off += align256(sizeof(int32_t) * 4 * (size_t)npts);
   w.counts = (unsigned*)(base + off);   off += align256(sizeof(unsigned) * 2 * (size_t)w.nblocks);
   w.offsets = (unsigned*)(base + off);  off += align256(sizeof(unsigned) * 2 * (size_t)w.nblocks);
-  w.minmax = (unsigned*)(base + off);   off += 256;
+  w.minmax = (float*)(base + off);      off += align256(sizeof(float) * 2 * (size_t)w.nblocks);
   w.totals = (int64_t*)(base + off);    off += 256;
   if (off > ws_bytes || !ws) return r3g_fail(ctx, R3G_E_WORKSPACE, "mc: workspace %zu < required %zu", ws_bytes, off);
   return R3G_OK;
@@ -367,7 +388,7 @@ extern "C" size_t r3g_mc_workspace_bytes(int n0, int n1, int n2) {
   const int64_t npts = (int64_t)n0 * n1 * n2;
   const int64_t ncells = (int64_t)(n0 - 1) * (n1 - 1) * (n2 - 1);
   const size_t nblocks = (size_t)((ncells + kThreads - 1) / kThreads);
-  return align256(sizeof(int32_t) * 4 * (size_t)npts) + 2 * align256(sizeof(unsigned) * 2 * nblocks) + 512;
+  return align256(sizeof(int32_t) * 4 * (size_t)npts) + 3 * align256(sizeof(unsigned) * 2 * nblocks) + 256;
 }
 
 extern "C" int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level, void* workspace,
@@ -381,8 +402,6 @@ extern "C" int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int
   if (rc) return rc;
   rc = carve(ctx, d, workspace, workspace_bytes, w);
   if (rc) return rc;
-  const unsigned init[2] = {0xFFFFFFFFu, 0u};
-  R3G_CUDA_OK(ctx, cudaMemcpyAsync(w.minmax, init, sizeof(init), cudaMemcpyHostToDevice, s));
   mc_count_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.counts, w.minmax);
   R3G_LAUNCH_OK(ctx);
   mc_scan_kernel<<<1, 1024, 0, s>>>(w.counts, w.offsets, w.nblocks, w.minmax, w.totals);
@@ -420,9 +439,9 @@ extern "C" int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, i
     rs.size[a] = bounds_host ? bounds_host[3 + a] - bounds_host[a] : 1.0;
     rs.n[a] = (double)nax[a];
   }
-  mc_vertex_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.vid, verts, rs);
+  mc_vertex_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.counts, w.vid, verts, rs);
   R3G_LAUNCH_OK(ctx);
-  mc_face_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.vid, faces);
+  mc_face_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.counts, w.vid, faces);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

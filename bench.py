@@ -126,38 +126,55 @@ def reference_arm(args):
 
 
 def instrumented_linear_roofline(pipe, cond, peak_tflops):
-    """Dominant kernel = linear_kernel (every nn.Linear of the DiT: 272 launches per forward).  One eager DiT
-    forward with a CUDA-event pair around every r3g_linear launch on the launching stream; algorithmic FLOPs =
-    2*M*N*K of each launch."""
+    """Dominant kernel = linear_kernel (every nn.Linear of the DiT: 275 launches per forward, 46 % of the step in
+    the ncu launch list).  Its launches are isolated from the other kernels of the forward -- same weights, same
+    order, same shapes/epilogues -- by recording one eager forward's r3g_linear calls and re-issuing exactly those
+    into a CUDA graph; the graph is replayed between CUDA events on the launching stream (no host gaps inside the
+    measured interval).  achieved = sum of 2*M*N*K over the launches / elapsed."""
     import torch
     from r3g import ops
-    recs = []
+    calls = []
     orig = ops.linear
 
-    def timed(x, w, bias=None, **kw):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = orig(x, w, bias, **kw)
-        b.record()
-        M = x.numel() // x.shape[-1]
-        recs.append((a, b, 2.0 * M * w.shape[0] * w.shape[1]))
-        return out
+    def record(x, w, bias=None, **kw):
+        calls.append((x, w, bias, kw))
+        return orig(x, w, bias, **kw)
 
     x = torch.randn(2, pipe.vae.latent_shape[0], pipe.vae.latent_shape[1], device="cuda").half()
     t = torch.full((2,), 0.5, device="cuda", dtype=torch.float16)
-    pipe.model(x, t, cond)  # warm
-    ops.linear = timed
+    ops.linear = record
     try:
         pipe.model(x, t, cond)
     finally:
         ops.linear = orig
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    fl = sum(f for _, _, f in recs)
-    achieved = fl / ms / 1e9
-    return {"bound": "tensor", "kernel": "linear_kernel<BN> (tcgen05 GEMM, gemm.cu)", "launches_timed": len(recs),
-            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-            "traffic": None, "avg_launch_ms": ms / len(recs), "flops_per_launch_avg": fl / len(recs)}
+    flops = sum(2.0 * (cx.numel() // cx.shape[-1]) * cw.shape[0] * cw.shape[1] for cx, cw, _, _ in calls)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for cx, cw, cb, kw in calls:
+            orig(cx, cw, cb, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(g):
+        for cx, cw, cb, kw in calls:
+            orig(cx, cw, cb, **kw)
+    for _ in range(3):
+        g.replay()
+    reps = 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    achieved = flops / ms / 1e9
+    return {"bound": "tensor", "kernel": "linear_kernel<BN> (tcgen05 GEMM, gemm.cu): the DiT forward's launches",
+            "launches_timed": len(calls), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / peak_tflops, "traffic": None, "avg_launch_ms": ms / len(calls),
+            "flops_per_launch_avg": flops / len(calls),
+            "note": "weights stream from HBM (2.2 GB per forward > L2); activations mostly L2-resident"}
 
 
 def main():

@@ -41,7 +41,8 @@ def timeit(fn, iters=10, warm=3, flush=True):
 def main():
     out = []
     torch.manual_seed(0)
-    for (M, N, K) in [(8884, 7168, 1024), (8884, 1024, 5120), (6144, 3072, 1024), (6144, 4096, 1024),
+    only = os.environ.get("R3G_MB_ONLY", "")
+    for (M, N, K) in [] if only and "linear" not in only else [(8884, 7168, 1024), (8884, 1024, 5120), (6144, 3072, 1024), (6144, 4096, 1024),
                       (6144, 1024, 4096), (2740, 3072, 1024), (32768, 4096, 1024), (32768, 1024, 4096),
                       (32768, 1024, 1024)]:
         x = torch.randn(M, K, device="cuda").half()
@@ -54,7 +55,7 @@ def main():
         out.append(dict(op="linear", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9, torch_ms=ms_t,
                         torch_tflops=fl / ms_t / 1e9))
         print(out[-1], flush=True)
-    for (B, H, Lq, Lk) in [(2, 16, 4442, 4442), (1, 16, 3072, 3072), (1, 16, 32768, 3072)]:
+    for (B, H, Lq, Lk) in [] if only and "attention" not in only else [(2, 16, 4442, 4442), (1, 16, 3072, 3072), (1, 16, 65536, 3072)]:
         q = torch.randn(B, Lq, H, 64, device="cuda").half()
         k = torch.randn(B, Lk, H, 64, device="cuda").half()
         v = torch.randn(B, Lk, H, 64, device="cuda").half()
@@ -66,7 +67,7 @@ def main():
         out.append(dict(op="attention", B=B, H=H, Lq=Lq, Lk=Lk, ms=ms, tflops=fl / ms / 1e9, torch_ms=ms_t,
                         torch_tflops=fl / ms_t / 1e9))
         print(out[-1], flush=True)
-    for n in (257, 513):
+    for n in [] if only and "mc" not in only else (257, 513):
         ax = torch.linspace(-1.01, 1.01, n, device="cuda")
         x, y, z = torch.meshgrid(ax, ax, ax, indexing="ij")
         vol = (0.25 - torch.sqrt((torch.sqrt(x * x + y * y) - 0.6) ** 2 + z * z)).contiguous()
@@ -77,7 +78,7 @@ def main():
                         grid_gbs=n ** 3 * 4 * 3 / ms / 1e6))
         print(out[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("R3G_MB_OUT", "microbench.json")), "w"), indent=1)
 
 
 if __name__ == "__main__":
