@@ -274,8 +274,7 @@ attention_kernel_v1(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 //     rescaled (TMEM load-multiply-store) only when the max grew by more than 2^8, so probabilities are bounded by
 //     256 (exact in the final normalisation, fp16-safe) and the common path never touches O;
 //   * exp2 on packed halves (ex2.approx.f16x2: two results per MUFU op, output already the fp16 P operand),
-//     3-input max, row sums accumulated as half2 partials and folded into fp32 every 32 columns;
-//   * setmaxnreg moves registers from the TMA/MMA warps to the softmax warps.
+//     3-input max, row sums accumulated as half2 partials and folded into fp32 every 16 columns.
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -308,9 +307,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
-__global__ void __launch_bounds__(kThreads, 2)
+constexpr int kThreadsV2 = 192;
+
+__global__ void __launch_bounds__(kThreadsV2, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -363,7 +376,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp == 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
     if (lane == 0) {
       mbar_expect_tx(q_full, kTileBytes);
       tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
@@ -379,7 +391,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else if (warp == 5) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
     constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
     constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);
     const uint32_t aq = smem_u32(sQ);
@@ -420,8 +431,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       __syncwarp();
     }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+  } else if (warp < 4) {
     const int row = threadIdx.x;
     const uint32_t lane_base = (uint32_t)(warp * 32);
     float m_used = -INFINITY, l_run = 0.f;
@@ -458,14 +468,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? ex2(m_used - m_new) : 1.f;
-#pragma unroll
-          for (int c = 0; c < kD; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
+#pragma unroll 1
+          for (int c = 0; c < kD; c += 8) {   // rare path: 8 columns at a time keeps the S row in registers
+            uint32_t o[8];
+            tmem_ld8(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st8(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
           }
           tmem_st_wait();
           l_run *= alpha;
@@ -474,31 +484,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < kBKV; c += 32) {
-        uint32_t pk[16];
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int c = 0; c < kBKV; c += 16) {
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint32_t e0 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
-                                                  fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
-          const uint32_t e1 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 2]), p.scale_log2, -m_used),
-                                                  fmaf(__uint_as_float(s[c + i + 3]), p.scale_log2, -m_used)));
-          const uint32_t e2 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 4]), p.scale_log2, -m_used),
-                                                  fmaf(__uint_as_float(s[c + i + 5]), p.scale_log2, -m_used)));
-          const uint32_t e3 = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i + 6]), p.scale_log2, -m_used),
-                                                  fmaf(__uint_as_float(s[c + i + 7]), p.scale_log2, -m_used)));
-          pk[(i >> 1) + 0] = e0; pk[(i >> 1) + 1] = e1; pk[(i >> 1) + 2] = e2; pk[(i >> 1) + 3] = e3;
-          a0 = hadd2_u32(a0, e0); a1 = hadd2_u32(a1, e1); a2 = hadd2_u32(a2, e2); a3 = hadd2_u32(a3, e3);
-        }
-        const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&a0));
-        const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&a1));
-        const float2 f2 = __half22float2(*reinterpret_cast<__half2*>(&a2));
-        const float2 f3 = __half22float2(*reinterpret_cast<__half2*>(&a3));
-        rs += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        for (int i = 0; i < 16; i += 2)
+          pk[i >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
+                                           fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+        const uint32_t a01 = hadd2_u32(hadd2_u32(pk[0], pk[1]), hadd2_u32(pk[2], pk[3]));
+        const uint32_t a23 = hadd2_u32(hadd2_u32(pk[4], pk[5]), hadd2_u32(pk[6], pk[7]));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
+        rs += (f0.x + f0.y) + (f1.x + f1.y);
         const uint32_t atom = p_row + (c >> 6) * (kBQ * 128);
         const int u0 = (c & 63) >> 3;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           const uint32_t addr = atom + (((u0 + q) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
                        "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
@@ -584,7 +584,7 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   if (use_v1)
     attention_kernel_v1<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   else
-    attention_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    attention_kernel<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -37,6 +37,8 @@ struct LinearParams {
   int64_t gate_ld;
   int gate_rows;
   const __half* residual;
+  const float* residual_f32;  // fp32 residual stream (VGGT blocks): y_f32 = res_f32 + ls_gamma[n] * fp16(acc + bias)
+  const float* ls_gamma;
   int out_f32;
   int tiles_m, tiles_n;
 };
@@ -250,6 +252,20 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
               }
             }
           }
+          if (p.residual_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + out_row * p.ldy + n0);
+            const float4* gp = reinterpret_cast<const float4*>(p.ls_gamma + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 r4 = rp[q];
+              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (p.ls_gamma) g4 = __ldg(gp + q);
+              f[4 * q + 0] = r4.x + g4.x * __half2float(__float2half_rn(f[4 * q + 0]));
+              f[4 * q + 1] = r4.y + g4.y * __half2float(__float2half_rn(f[4 * q + 1]));
+              f[4 * q + 2] = r4.z + g4.z * __half2float(__float2half_rn(f[4 * q + 2]));
+              f[4 * q + 3] = r4.w + g4.w * __half2float(__float2half_rn(f[4 * q + 3]));
+            }
+          }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_row * p.ldy + n0);
 #pragma unroll
@@ -310,7 +326,9 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.tiles_per_seg = (seg_len + BM - 1) / BM;
   p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
   p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
-  p.residual = (const __half*)a->residual;
+  p.residual = a->residual_f32 ? nullptr : (const __half*)a->residual;
+  p.residual_f32 = a->residual_f32 ? (const float*)a->residual : nullptr;
+  p.ls_gamma = (const float*)a->ls_gamma;
   p.out_f32 = a->out_f32;
   p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = (a->N + BN - 1) / BN;
@@ -337,7 +355,9 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
     return r3g_fail(ctx, R3G_E_INVALID, "linear: need N %% 32 == 0, K %% 8 == 0, ldx/ldy %% 8 == 0 (N=%d K=%d)", a->N,
                     a->K);
   if (a->seg_len > 0 && a->M % a->seg_len) return r3g_fail(ctx, R3G_E_INVALID, "linear: M must be a multiple of seg_len");
-  if (a->residual && a->out_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: residual with fp32 output unsupported");
+  if (a->residual && (a->out_f32 != 0) != (a->residual_f32 != 0))
+    return r3g_fail(ctx, R3G_E_INVALID, "linear: an fp32 output takes an fp32 residual (residual_f32=1) and vice versa");
+  if (a->ls_gamma && !a->residual_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: ls_gamma needs the fp32 residual form");
   if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
   cudaStream_t s = (cudaStream_t)stream;
   // tile width: widest tile that still gives every SM work

@@ -173,6 +173,157 @@ __global__ void __launch_bounds__(256) qk_norm_kernel(__half* __restrict__ buf, 
   if (active) *reinterpret_cast<Half8*>(p) = pack8(o);
 }
 
+// ------------------------------------------------------------------------------------------- LayerNorm, fp32 input
+__global__ void __launch_bounds__(256) layernorm_f32in_kernel(const float* __restrict__ x, int64_t ldx,
+                                                              __half* __restrict__ y, int64_t ldy, int rows,
+                                                              int width, float eps, const __half* __restrict__ w,
+                                                              const __half* __restrict__ b) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = width >> 3;
+  float v[kLnMaxChunks][8];
+  float s = 0.f;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * ldx);
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      const float4 a = xr[2 * c], bb = xr[2 * c + 1];
+      v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+      v[j][4] = bb.x; v[j][5] = bb.y; v[j][6] = bb.z; v[j][7] = bb.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = v[j][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
+  Half8* yr = reinterpret_cast<Half8*>(y + (int64_t)row * ldy);
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) {
+      float o[8], wf[8], bf[8];
+      if (w) unpack8(reinterpret_cast<const Half8*>(w)[c], wf);
+      if (b) unpack8(reinterpret_cast<const Half8*>(b)[c], bf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = (v[j][i] - mean) * rstd;
+        if (w) t *= wf[i];
+        if (b) t += bf[i];
+        o[i] = t;
+      }
+      yr[c] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- q/k LayerNorm + 2-D RoPE
+// 8 lanes per (row, head, q|k) group of 64 features; lanes 0-3 hold the "vertical" half, 4-7 the "horizontal" one;
+// inside a half the rotation partner of feature i is i +- 16, i.e. the lane 2 apart.
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(__half* __restrict__ qkv, int64_t ld, int64_t ngroups,
+                                                           int heads, float eps, const __half* __restrict__ q_w,
+                                                           const __half* __restrict__ q_b,
+                                                           const __half* __restrict__ k_w,
+                                                           const __half* __restrict__ k_b, float rope_freq,
+                                                           int tokens_per_frame, int n_special, int patches_w) {
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool active = grp < ngroups;
+  const int64_t g = active ? grp : 0;
+  const int sel = (int)(g & 1);
+  const int64_t rh = g >> 1;
+  const int h = (int)(rh % heads);
+  const int64_t row = rh / heads;
+  __half* p = qkv + row * ld + (int64_t)sel * heads * 64 + (int64_t)h * 64 + sub * 8;
+  float f[8];
+  unpack8(*reinterpret_cast<const Half8*>(p), f);
+  const __half* wv = sel ? k_w : q_w;
+  const __half* bv = sel ? k_b : q_b;
+  if (wv) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mean = s * (1.f / 64.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float d = f[i] - mean;
+      q += d * d;
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    const float rstd = rsqrtf(q * (1.f / 64.f) + eps);
+    float wf[8], bf[8];
+    unpack8(reinterpret_cast<const Half8*>(wv)[sub], wf);
+    if (bv) unpack8(reinterpret_cast<const Half8*>(bv)[sub], bf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * wf[i] + (bv ? bf[i] : 0.f);
+  }
+  float partner[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) partner[i] = __shfl_xor_sync(0xffffffffu, f[i], 2);
+  if (rope_freq > 0.f) {
+    const int tok = (int)(row % tokens_per_frame);
+    int py = 0, px = 0;
+    if (tok >= n_special) {
+      const int pidx = tok - n_special;
+      py = pidx / patches_w + 1;
+      px = pidx % patches_w + 1;
+    }
+    const float pos = (float)((sub < 4) ? py : px);
+    const int within = (sub & 3) * 8;      // feature index inside the 32-wide half
+    const bool upper = within >= 16;       // second 16: rotate_features gives +x1, first 16: -x2
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = (within + i) & 15;     // frequency index
+      const float inv_freq = 1.f / powf(rope_freq, (float)(2 * j) / 32.f);
+      const float ang = pos * inv_freq;
+      float sn, cs;
+      sincosf(ang, &sn, &cs);
+      const float rot = upper ? partner[i] : -partner[i];
+      f[i] = f[i] * cs + rot * sn;
+    }
+  }
+  if (active) *reinterpret_cast<Half8*>(p) = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------- patchify
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __half* __restrict__ out,
+                                                       int64_t out_ld, int N, int H, int W, int ps, float m0, float m1,
+                                                       float m2, float s0, float s1, float s2) {
+  const int hp = H / ps, wp = W / ps, kk = 3 * ps * ps;
+  const int64_t row = blockIdx.x;   // one block per patch
+  const int n = (int)(row / (hp * wp)), pr = (int)(row % (hp * wp));
+  const int y0 = (pr / wp) * ps, x0 = (pr % wp) * ps;
+  for (int col = threadIdx.x; col < out_ld; col += blockDim.x) {
+    float v = 0.f;
+    if (col < kk) {
+      const int c = col / (ps * ps), r = col % (ps * ps);
+      const float px = img[(((int64_t)n * 3 + c) * H + y0 + r / ps) * W + x0 + r % ps];
+      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      v = (px - mean) / sd;
+    }
+    out[row * out_ld + col] = __float2half_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- GEMV (M <= 8)
 constexpr int kGemvMaxB = 8;
 __global__ void __launch_bounds__(256) gemv_kernel(const __half* __restrict__ w, const __half* __restrict__ bias,
@@ -448,6 +599,49 @@ extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, 
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ldx, (__half*)y, ldy, rows, width, eps, (const __half*)w, (const __half*)b,
       (const __half*)scale, (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride, y_seg_stride);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_layernorm_f32in(r3g_ctx* ctx, const float* x, int64_t ldx, void* y, int64_t ldy, int rows,
+                                   int width, float eps, const void* w, const void* b, void* stream) {
+  R3G_NEED_GPU(ctx, "layernorm_f32in");
+  if (width % 8 || width > kLnMaxChunks * 256 || ldx % 4 || ldy % 8)
+    return r3g_fail(ctx, R3G_E_INVALID, "layernorm_f32in: width %d must be a multiple of 8 and <= %d", width,
+                    kLnMaxChunks * 256);
+  if (rows <= 0) return R3G_OK;
+  layernorm_f32in_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ldx, (__half*)y, ldy, rows, width, eps,
+                                                                             (const __half*)w, (const __half*)b);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_qk_norm_rope(r3g_ctx* ctx, void* qkv, int64_t ld, int64_t rows, int heads, float eps,
+                                const void* q_w, const void* q_b, const void* k_w, const void* k_b, float rope_freq,
+                                int tokens_per_frame, int n_special, int patches_w, void* stream) {
+  R3G_NEED_GPU(ctx, "qk_norm_rope");
+  if (ld % 8 || (q_w == nullptr) != (k_w == nullptr) || tokens_per_frame < 1 || patches_w < 1)
+    return r3g_fail(ctx, R3G_E_INVALID, "qk_norm_rope: bad arguments");
+  const int64_t ngroups = rows * heads * 2;
+  if (ngroups <= 0) return R3G_OK;
+  qk_norm_rope_kernel<<<(unsigned)((ngroups * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (__half*)qkv, ld, ngroups, heads, eps, (const __half*)q_w, (const __half*)q_b, (const __half*)k_w,
+      (const __half*)k_b, rope_freq, tokens_per_frame, n_special, patches_w);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_patchify(r3g_ctx* ctx, const float* images, void* out, int64_t out_ld, int N, int H, int W,
+                            int patch, const float* mean3_host, const float* std3_host, void* stream) {
+  R3G_NEED_GPU(ctx, "patchify");
+  if (!images || !out || patch < 1 || H % patch || W % patch || out_ld < 3 * patch * patch)
+    return r3g_fail(ctx, R3G_E_INVALID, "patchify: bad arguments");
+  const float m[3] = {mean3_host ? mean3_host[0] : 0.f, mean3_host ? mean3_host[1] : 0.f, mean3_host ? mean3_host[2] : 0.f};
+  const float sd[3] = {std3_host ? std3_host[0] : 1.f, std3_host ? std3_host[1] : 1.f, std3_host ? std3_host[2] : 1.f};
+  const int64_t rows = (int64_t)N * (H / patch) * (W / patch);
+  if (rows <= 0) return R3G_OK;
+  patchify_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(images, (__half*)out, out_ld, N, H, W, patch, m[0],
+                                                                     m[1], m[2], sd[0], sd[1], sd[2]);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

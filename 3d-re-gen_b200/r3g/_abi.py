@@ -26,6 +26,8 @@ class LinearArgs(C.Structure):
         ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("gate_rows", C.c_int),
         ("residual", C.c_void_p),
         ("out_f32", C.c_int),
+        ("residual_f32", C.c_int),
+        ("ls_gamma", C.c_void_p),
     ]
 
 
@@ -56,6 +58,9 @@ SIGNATURES = {
     "r3g_linear": (_i, [_vp, C.POINTER(LinearArgs), _vp]),
     "r3g_attention": (_i, [_vp, C.POINTER(AttentionArgs), _vp]),
     "r3g_layernorm": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _vp]),
+    "r3g_layernorm_f32in": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp]),
+    "r3g_qk_norm_rope": (_i, [_vp, _vp, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "r3g_patchify": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "r3g_qk_norm": (_i, [_vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "r3g_gemv": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "r3g_timestep_embedding": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp]),

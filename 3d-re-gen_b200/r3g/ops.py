@@ -67,7 +67,7 @@ def _merge_seg(xs, ys, name):
 
 
 def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
-           out_dtype=torch.float16):
+           ls_gamma=None, out_dtype=torch.float16):
     """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
 
     x: [..., K] or a strided [M, K] / [S, L, K] view, w: [N, K] contiguous, out: same row structure, width N.
@@ -97,7 +97,14 @@ def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None,
         _f16(gate, "gate")
         a.gate, a.gate_ld, a.gate_rows = gate.data_ptr(), gate.stride(0), gate_rows
     if residual is not None:
-        _f16(residual, "residual")
+        if residual.dtype == torch.float32:
+            a.residual_f32 = 1
+            if ls_gamma is not None:
+                if ls_gamma.dtype != torch.float32 or ls_gamma.numel() != N:
+                    raise TypeError("ls_gamma must be float32 [N]")
+                a.ls_gamma = ls_gamma.data_ptr()
+        else:
+            _f16(residual, "residual")
         r2, _, _, ldr, rl, rst = _rows(residual, "residual")
         if ldr != ldy or (rl, rst) != (yl, yst):
             raise ValueError("residual must share out's geometry")
@@ -146,6 +153,51 @@ def layernorm(x, weight=None, bias=None, eps=1e-6, scale=None, shift=None, rows_
     ctx.check(ctx.lib.r3g_layernorm(ctx.handle, _p(x2), ldx, _p(o2), ldy, rows, width, float(eps), _p(weight),
                                     _p(bias), _p(scale), _p(shift), mod_ld, int(rows_per_batch), seg_len, xs, ys,
                                     _stream()))
+    return out
+
+
+def layernorm_f32in(x, weight, bias, eps=1e-5, out=None):
+    """LayerNorm of a float32 [rows, width] stream into fp16 (VGGT blocks keep the residual stream in fp32)."""
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("x must be contiguous float32")
+    ctx = _ctx(x)
+    width = x.shape[-1]
+    rows = x.numel() // width
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    ctx.check(ctx.lib.r3g_layernorm_f32in(ctx.handle, _p(x), width, _p(out), out.stride(-2) if out.dim() > 1 else width,
+                                          rows, width, float(eps), _p(weight), _p(bias), _stream()))
+    return out
+
+
+def qk_norm_rope_(qkv, heads, eps, q_w, q_b, k_w, k_b, rope_freq, tokens_per_frame, n_special, patches_w):
+    """In place on a packed fp16 [rows, 3*H*64] (3,H,D) projection: q/k LayerNorm (if weights) + 2-D RoPE (if freq>0)."""
+    _f16(qkv, "qkv")
+    ctx = _ctx(qkv)
+    if not qkv.is_contiguous():
+        raise ValueError("qkv must be contiguous")
+    ld = qkv.shape[-1]
+    rows = qkv.numel() // ld
+    ctx.check(ctx.lib.r3g_qk_norm_rope(ctx.handle, _p(qkv), ld, rows, heads, float(eps), _p(q_w), _p(q_b), _p(k_w),
+                                       _p(k_b), float(rope_freq), int(tokens_per_frame), int(n_special),
+                                       int(patches_w), _stream()))
+    return qkv
+
+
+def patchify(images, patch, mean=None, std=None, out_ld=None):
+    """images float32 [N,3,H,W] -> fp16 [N*(H/p)*(W/p), out_ld] rows in Conv2d weight order (zero padded)."""
+    if images.dtype != torch.float32 or images.dim() != 4 or images.shape[1] != 3:
+        raise TypeError("images must be float32 [N,3,H,W]")
+    images = images.contiguous()
+    ctx = _ctx(images)
+    N, _, H, W = images.shape
+    kk = 3 * patch * patch
+    out_ld = out_ld or ((kk + 7) // 8) * 8
+    out = torch.empty(N * (H // patch) * (W // patch), out_ld, device=images.device, dtype=torch.float16)
+    m = (C.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+    sd = (C.c_float * 3)(*(std if std is not None else (1.0, 1.0, 1.0)))
+    ctx.check(ctx.lib.r3g_patchify(ctx.handle, _p(images), _p(out), out_ld, N, H, W, int(patch), C.cast(m, C.c_void_p),
+                                   C.cast(sd, C.c_void_p), _stream()))
     return out
 
 

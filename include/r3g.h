@@ -82,6 +82,9 @@ int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, flo
  *        residuals of hunyuan3ddit.py:212-216,267 and the plain residuals of attention_blocks.py:296-299.
  *        residual uses Y's row mapping and may alias Y.
  *   out_f32: 0 -> Y is fp16, 1 -> Y is float32.
+ *   residual_f32 / ls_gamma: the VGGT block form (vggt/layers/block.py:77-98 under autocast): the residual stream is
+ *        float32, `residual` then points to float32 with Y's geometry (Y float32, may alias), and
+ *        Y = residual + ls_gamma[n] * fp16(acc + bias)  with ls_gamma the float32 LayerScale vector (NULL = 1).
  */
 typedef struct {
   const void* x; int64_t ldx;
@@ -92,8 +95,10 @@ typedef struct {
   int seg_len; int64_t x_seg_stride, y_seg_stride;
   int act, act_col0, act_col1;
   const void* gate; int64_t gate_ld; int gate_rows;
-  const void* residual;      /* fp16, same geometry as y */
+  const void* residual;      /* fp16 (or float32 if residual_f32), same geometry as y */
   int out_f32;
+  int residual_f32;
+  const void* ls_gamma;      /* float32 [N] or NULL */
 } r3g_linear_args;
 int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream);
 
@@ -122,6 +127,22 @@ int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* stream);
 int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width, float eps,
                   const void* w, const void* b, const void* scale, const void* shift, int64_t mod_ld,
                   int rows_per_batch, int seg_len, int64_t x_seg_stride, int64_t y_seg_stride, void* stream);
+/* Same with a float32 input (the VGGT residual stream, vggt/layers/block.py:79,82); y is fp16. */
+int r3g_layernorm_f32in(r3g_ctx* ctx, const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int width,
+                        float eps, const void* w, const void* b, void* stream);
+/* VGGT attention prologue, in place on a packed fp16 [rows, 3*H*64] projection laid out (3, H, D)
+ * (vggt/layers/attention.py:52-59): LayerNorm(64, eps) with affine q_w/q_b, k_w/k_b on q and k (NULL weights skip
+ * the norm), then 2-D rotary embedding (vggt/layers/rope.py:62-188, base `rope_freq`, first half of D by the y
+ * position, second half by x) when rope_freq > 0.  Row r is token (r % tokens_per_frame); tokens below n_special
+ * sit at position (0,0), patch p at (p / patches_w + 1, p % patches_w + 1) (aggregator.py:216-228). */
+int r3g_qk_norm_rope(r3g_ctx* ctx, void* qkv, int64_t ld, int64_t rows, int heads, float eps, const void* q_w,
+                     const void* q_b, const void* k_w, const void* k_b, float rope_freq, int tokens_per_frame,
+                     int n_special, int patches_w, void* stream);
+/* Patch extraction for the ViT patch embedding (vggt/layers/patch_embed.py:72-85 as a GEMM): images float32
+ * [N,3,H,W]; each value is normalised (v - mean[c]) / std[c] first (aggregator.py:199-200; pass mean 0 / std 1 to
+ * skip); out fp16 [N*(H/ps)*(W/ps), out_ld] with column c*ps*ps + py*ps + px (Conv2d weight order), zero padded. */
+int r3g_patchify(r3g_ctx* ctx, const float* images, void* out, int64_t out_ld, int N, int H, int W, int patch,
+                 const float* mean3_host, const float* std3_host, void* stream);
 /* In-place per-head normalisation of q and k inside a packed projection output.
  * Element (r, h, d) of q lives at buf + r*ld + q_off + h*head_stride + d (same for k with k_off).
  * mode 0: RMSNorm over d with learned scale, computed in fp32, rounded to fp16, THEN multiplied by the fp16

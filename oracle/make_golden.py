@@ -21,11 +21,11 @@ import ref_import  # noqa: E402
 OUT = os.path.join(HERE, "..", "tests", "golden")
 
 
-def fp16_round_(module):
+def fp16_round_(module, buffers=True):
     with torch.no_grad():
         for p in module.parameters():
             p.copy_(p.half().float())
-        for b in module.buffers():
+        for b in module.buffers() if buffers else ():
             if b.is_floating_point():
                 b.copy_(b.half().float())
 
@@ -172,6 +172,55 @@ def golden_unproject():
     print("unproject:", pts.shape, pts.dtype)
 
 
+def golden_vggt():
+    ref_import.vggt_package()
+    from vggt.models.aggregator import Aggregator
+    from vggt.layers.vision_transformer import DinoVisionTransformer
+    from vggt.layers.block import Block
+    torch.manual_seed(4)
+    agg = Aggregator(img_size=56, patch_size=14, embed_dim=128, depth=2, num_heads=2, patch_embed="conv",
+                     qk_norm=True, rope_freq=100, init_values=0.01).eval()
+    with torch.no_grad():
+        for n, prm in agg.named_parameters():
+            if "gamma" in n:
+                prm.copy_(0.5 + 0.2 * torch.randn_like(prm))      # LayerScale that matters
+            elif "norm" in n:
+                prm.copy_((1.0 if n.endswith("weight") else 0.0) + 0.2 * torch.randn_like(prm))
+            elif n in ("camera_token", "register_token"):
+                prm.copy_(0.5 * torch.randn_like(prm))
+            elif n.endswith("bias"):
+                prm.copy_(0.1 * torch.randn_like(prm))
+    fp16_round_(agg, buffers=False)  # the ImageNet mean/std buffers are constants, not checkpoint weights
+    imgs = torch.rand(1, 2, 3, 56, 70)
+    with torch.no_grad():
+        outs, psi = agg(imgs)
+    d = sd_np(agg, "agg.")
+    d.update(agg_images=imgs.numpy(), agg_psi=np.int64(psi))
+    for i, o in enumerate(outs):
+        d[f"agg_out{i}"] = o.numpy()
+    torch.manual_seed(5)
+    vit = DinoVisionTransformer(img_size=56, patch_size=14, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4,
+                                num_register_tokens=4, init_values=1.0, block_fn=Block, interpolate_antialias=True,
+                                interpolate_offset=0.0, block_chunks=0).eval()
+    with torch.no_grad():
+        for n, prm in vit.named_parameters():
+            if "gamma" in n:
+                prm.copy_(0.5 + 0.2 * torch.randn_like(prm))
+            elif n in ("cls_token", "register_tokens", "pos_embed"):
+                prm.copy_(0.3 * torch.randn_like(prm))
+            elif n.endswith("bias"):
+                prm.copy_(0.1 * torch.randn_like(prm))
+    fp16_round_(vit)
+    for tag, shape in (("native", (2, 3, 56, 56)), ("interp", (2, 3, 70, 56))):
+        x = torch.randn(*shape)
+        with torch.no_grad():
+            y = vit.forward_features(x)["x_norm_patchtokens"]
+        d[f"vit_x_{tag}"], d[f"vit_y_{tag}"] = x.numpy(), y.numpy()
+    d.update(sd_np(vit, "vit."))
+    np.savez_compressed(os.path.join(OUT, "vggt_mini.npz"), **d)
+    print("vggt_mini: outs", len(outs), tuple(outs[0].shape))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "reference checkout not found"
     os.makedirs(OUT, exist_ok=True)
@@ -180,3 +229,4 @@ if __name__ == "__main__":
     golden_vae()
     golden_scheduler()
     golden_unproject()
+    golden_vggt()

@@ -1,0 +1,86 @@
+"""GPU: the VGGT aggregator mirror (fp16 tensor-core operands, fp32 residual stream) against the fixture produced
+by the reference's own Aggregator / DinoVisionTransformer modules, and at full width against the fp32 oracle.
+Tolerance: the reference itself runs this under bf16 autocast (8 mantissa bits); we require rel-L2 <= 5e-3
+against the fp32 ground truth."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float().flatten().cpu(), b.float().flatten().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def test_qk_norm_rope_kernel_against_oracle():
+    import vggt_ref as V
+    from r3g import ops
+    torch.manual_seed(0)
+    Bf, hp, wp, H = 3, 4, 5, 2
+    P = hp * wp + 5
+    qkv = torch.randn(Bf * P, 3 * H * 64, device="cuda").half()
+    qw, qb = (1 + 0.2 * torch.randn(64, device="cuda")).half(), (0.1 * torch.randn(64, device="cuda")).half()
+    kw, kb = (1 + 0.2 * torch.randn(64, device="cuda")).half(), (0.1 * torch.randn(64, device="cuda")).half()
+    ref = qkv.float().view(Bf, P, 3, H, 64).permute(2, 0, 3, 1, 4).clone()
+    q = torch.nn.functional.layer_norm(ref[0], (64,), qw.float(), qb.float(), 1e-5)
+    k = torch.nn.functional.layer_norm(ref[1], (64,), kw.float(), kb.float(), 1e-5)
+    ys, xs = torch.meshgrid(torch.arange(hp), torch.arange(wp), indexing="ij")
+    pos = torch.cat([torch.zeros(5, 2, dtype=torch.long), torch.stack((ys, xs), -1).reshape(-1, 2) + 1])[None].expand(Bf, -1, -1).cuda()
+    q, k = V.rope_2d(q, pos, 100.0), V.rope_2d(k, pos, 100.0)
+    out = ops.qk_norm_rope_(qkv.clone(), H, 1e-5, qw, qb, kw, kb, 100.0, P, 5, wp).float().view(Bf, P, 3, H, 64)
+    assert (out[:, :, 0].permute(0, 2, 1, 3) - q).abs().max().item() < 6e-3
+    assert (out[:, :, 1].permute(0, 2, 1, 3) - k).abs().max().item() < 6e-3
+    assert torch.equal(out[:, :, 2], qkv.float().view(Bf, P, 3, H, 64)[:, :, 2])
+
+
+def test_aggregator_and_dino_mini_against_reference_fixture(golden_dir):
+    from r3g.vggt import Aggregator, DinoVisionTransformer
+    z = np.load(os.path.join(golden_dir, "vggt_mini.npz"))
+    sd = {k[len("w:agg."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:agg.")}
+    agg = Aggregator(img_size=56, patch_size=14, embed_dim=128, depth=2, num_heads=2, patch_embed="conv")
+    agg.load_state_dict(sd)
+    outs, psi = agg(torch.from_numpy(z["agg_images"]).cuda())
+    assert psi == int(z["agg_psi"]) and len(outs) == 2
+    for i, o in enumerate(outs):
+        assert o.dtype == torch.float32 and tuple(o.shape) == z[f"agg_out{i}"].shape
+        assert rel_l2(o, torch.from_numpy(z[f"agg_out{i}"])) < 5e-3
+    vsd = {k[len("w:vit."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:vit.")}
+    vit = DinoVisionTransformer(vsd, "", 128, 2, 2, 14, 4, torch.device("cuda"))
+    for tag in ("native", "interp"):
+        x = torch.from_numpy(z[f"vit_x_{tag}"]).cuda()
+        n, _, hh, ww = x.shape
+        rows = n * ((hh // 14) * (ww // 14) + 5)
+        e = lambda *s: torch.empty(*s, device="cuda", dtype=torch.float16)  # noqa: E731
+        ws = dict(xn=e(rows, 128), qkv=e(rows, 384), hid=e(rows, 512))
+        y = vit.forward_patch_tokens(x, None, None, ws)
+        assert rel_l2(y, torch.from_numpy(z[f"vit_y_{tag}"])) < 5e-3
+
+
+def test_aggregator_full_width_against_oracle():
+    """embed 1024 / 16 heads / 518x518 (1374 tokens per frame), S = 2, 2+2 alternating blocks, conv patch embed."""
+    import vggt_ref as V
+    from r3g.vggt import Aggregator
+    torch.manual_seed(1)
+    C, depth = 1024, 2
+    sd = {"patch_embed.proj.weight": torch.randn(C, 3, 14, 14) * 0.02, "patch_embed.proj.bias": torch.randn(C) * 0.02,
+          "camera_token": torch.randn(1, 2, 1, C) * 0.5, "register_token": torch.randn(1, 2, 4, C) * 0.5}
+    for kind in ("frame", "global"):
+        for i in range(depth):
+            p = f"{kind}_blocks.{i}."
+            for n, shp, s in (("attn.qkv", (3 * C, C), 0.02), ("attn.proj", (C, C), 0.02), ("mlp.fc1", (4 * C, C), 0.02),
+                              ("mlp.fc2", (C, 4 * C), 0.02)):
+                sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.randn(*shp) * s, torch.randn(shp[0]) * 0.02
+            for n, d in (("norm1", C), ("norm2", C), ("attn.q_norm", 64), ("attn.k_norm", 64)):
+                sd[p + n + ".weight"], sd[p + n + ".bias"] = 1 + 0.1 * torch.randn(d), 0.05 * torch.randn(d)
+            sd[p + "ls1.gamma"], sd[p + "ls2.gamma"] = 0.5 + 0.1 * torch.randn(C), 0.5 + 0.1 * torch.randn(C)
+    sd = {k: v.half().float() for k, v in sd.items()}
+    imgs = torch.rand(1, 2, 3, 518, 518, device="cuda")
+    agg = Aggregator(depth=depth, patch_embed="conv").load_state_dict(sd)
+    outs, _ = agg(imgs)
+    ref = V.aggregator({k: v.cuda() for k, v in sd.items()}, imgs, depth, 16)
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) < 5e-3

@@ -84,3 +84,16 @@ def test_live_reference_modules_agree_with_fixtures(golden_dir):
     with torch.no_grad():
         y = model(torch.from_numpy(z["x"]), torch.from_numpy(z["t"]), {"main": torch.from_numpy(z["cond"])})
     np.testing.assert_allclose(y.numpy(), z["y"], rtol=0, atol=1e-6)
+
+
+def test_vggt_restatement_matches_reference_fixture(golden_dir):
+    import vggt_ref as V
+    z = np.load(os.path.join(golden_dir, "vggt_mini.npz"))
+    sd = {k[len("w:agg."):]: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith("w:agg.")}
+    outs = V.aggregator(sd, torch.from_numpy(z["agg_images"]), depth=2, heads=2)
+    for i, o in enumerate(outs):
+        np.testing.assert_allclose(o.numpy(), z[f"agg_out{i}"], rtol=0, atol=3e-5)
+    vsd = {k[len("w:vit."):]: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith("w:vit.")}
+    for tag in ("native", "interp"):
+        y = V.dino_patch_tokens(vsd, "", torch.from_numpy(z[f"vit_x_{tag}"]), 2, 2, 14, 4)
+        np.testing.assert_allclose(y.numpy(), z[f"vit_y_{tag}"], rtol=0, atol=3e-5)
