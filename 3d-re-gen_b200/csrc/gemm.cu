@@ -11,6 +11,7 @@
 // ShapeVAE c_qkv/c_proj/c_fc (attention_blocks.py:166-182,345-363), geo-decoder query_proj/c_q/c_kv/c_proj/mlp
 // (attention_blocks.py:250-261,484-494).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "r3g_internal.h"
 #include "r3g_ptx.cuh"
@@ -84,6 +85,94 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   const float e = ex2f(az * az * -1.4426950408889634f);
   const float erf_abs = fmaf(-pl, e, 1.f);
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;   // x>0: 0.5x(1+erf), x<0: 0.5x(1-erf|.|)
+}
+
+// One 32-column chunk of one accumulator row: v = fp32 accumulators of columns [n0, n0+32) of logical row r.
+__device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint32_t* v, int r, int64_t out_row,
+                                               int n0, const __half* gate_row) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias) {
+      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 b4 = __ldg(bp + q);
+        const __half2* h = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __half22float2(h[j]);
+          f[q * 8 + 2 * j] += t.x;
+          f[q * 8 + 2 * j + 1] += t.y;
+        }
+      }
+    }
+    if (p.act && n0 < p.act_col1 && n0 + 32 > p.act_col0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + j;
+        if (n >= p.act_col0 && n < p.act_col1) {
+          // the reference's Linear output is fp16 before the activation sees it
+          const float xh = __half2float(__float2half_rn(f[j]));
+          f[j] = (p.act == 1) ? gelu_tanh_f(xh) : gelu_erf_f(xh);
+        }
+      }
+    }
+    if (p.residual) {
+      const __half* rp = p.residual + out_row * p.ldy + n0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 r4 = *reinterpret_cast<const uint4*>(rp + 8 * q);
+        const __half2* h = reinterpret_cast<const __half2*>(&r4);
+        uint4 g4 = make_uint4(0, 0, 0, 0);
+        if (gate_row) g4 = __ldg(reinterpret_cast<const uint4*>(gate_row + n0) + q);
+        const __half2* gh = reinterpret_cast<const __half2*>(&g4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 rr = __half22float2(h[j]);
+          float y0 = __half2float(__float2half_rn(f[q * 8 + 2 * j]));
+          float y1 = __half2float(__float2half_rn(f[q * 8 + 2 * j + 1]));
+          if (gate_row) {
+            float2 gg = __half22float2(gh[j]);
+            y0 = __half2float(__float2half_rn(gg.x * y0));
+            y1 = __half2float(__float2half_rn(gg.y * y1));
+          }
+          f[q * 8 + 2 * j] = rr.x + y0;
+          f[q * 8 + 2 * j + 1] = rr.y + y1;
+        }
+      }
+    }
+    if (p.residual_f32) {
+      const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + out_row * p.ldy + n0);
+      const float4* gp = reinterpret_cast<const float4*>(p.ls_gamma + n0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 r4 = rp[q];
+        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.ls_gamma) g4 = __ldg(gp + q);
+        f[4 * q + 0] = r4.x + g4.x * __half2float(__float2half_rn(f[4 * q + 0]));
+        f[4 * q + 1] = r4.y + g4.y * __half2float(__float2half_rn(f[4 * q + 1]));
+        f[4 * q + 2] = r4.z + g4.z * __half2float(__float2half_rn(f[4 * q + 2]));
+        f[4 * q + 3] = r4.w + g4.w * __half2float(__float2half_rn(f[4 * q + 3]));
+      }
+    }
+    if (p.out_f32) {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_row * p.ldy + n0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + out_row * p.ldy + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_half2(f[8 * q + 0], f[8 * q + 1]);
+        o.y = pack_half2(f[8 * q + 2], f[8 * q + 3]);
+        o.z = pack_half2(f[8 * q + 4], f[8 * q + 5]);
+        o.w = pack_half2(f[8 * q + 6], f[8 * q + 7]);
+        op[q] = o;
+      }
+    }
+
 }
 
 template <int BN>
@@ -199,90 +288,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0), v);
         tmem_ld_wait();
-        if (row_ok) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 b4 = __ldg(bp + q);
-              const __half2* h = reinterpret_cast<const __half2*>(&b4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 t = __half22float2(h[j]);
-                f[q * 8 + 2 * j] += t.x;
-                f[q * 8 + 2 * j + 1] += t.y;
-              }
-            }
-          }
-          if (p.act && n0 < p.act_col1 && n0 + 32 > p.act_col0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              if (n >= p.act_col0 && n < p.act_col1) {
-                // the reference's Linear output is fp16 before the activation sees it
-                const float xh = __half2float(__float2half_rn(f[j]));
-                f[j] = (p.act == 1) ? gelu_tanh_f(xh) : gelu_erf_f(xh);
-              }
-            }
-          }
-          if (p.residual) {
-            const __half* rp = p.residual + out_row * p.ldy + n0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 r4 = *reinterpret_cast<const uint4*>(rp + 8 * q);
-              const __half2* h = reinterpret_cast<const __half2*>(&r4);
-              uint4 g4 = make_uint4(0, 0, 0, 0);
-              if (gate_row) g4 = __ldg(reinterpret_cast<const uint4*>(gate_row + n0) + q);
-              const __half2* gh = reinterpret_cast<const __half2*>(&g4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 rr = __half22float2(h[j]);
-                float y0 = __half2float(__float2half_rn(f[q * 8 + 2 * j]));
-                float y1 = __half2float(__float2half_rn(f[q * 8 + 2 * j + 1]));
-                if (gate_row) {
-                  float2 gg = __half22float2(gh[j]);
-                  y0 = __half2float(__float2half_rn(gg.x * y0));
-                  y1 = __half2float(__float2half_rn(gg.y * y1));
-                }
-                f[q * 8 + 2 * j] = rr.x + y0;
-                f[q * 8 + 2 * j + 1] = rr.y + y1;
-              }
-            }
-          }
-          if (p.residual_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + out_row * p.ldy + n0);
-            const float4* gp = reinterpret_cast<const float4*>(p.ls_gamma + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 r4 = rp[q];
-              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (p.ls_gamma) g4 = __ldg(gp + q);
-              f[4 * q + 0] = r4.x + g4.x * __half2float(__float2half_rn(f[4 * q + 0]));
-              f[4 * q + 1] = r4.y + g4.y * __half2float(__float2half_rn(f[4 * q + 1]));
-              f[4 * q + 2] = r4.z + g4.z * __half2float(__float2half_rn(f[4 * q + 2]));
-              f[4 * q + 3] = r4.w + g4.w * __half2float(__float2half_rn(f[4 * q + 3]));
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_row * p.ldy + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + out_row * p.ldy + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_half2(f[8 * q + 0], f[8 * q + 1]);
-              o.y = pack_half2(f[8 * q + 2], f[8 * q + 3]);
-              o.z = pack_half2(f[8 * q + 4], f[8 * q + 5]);
-              o.w = pack_half2(f[8 * q + 6], f[8 * q + 7]);
-              op[q] = o;
-            }
-          }
-        }
+        if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -345,6 +351,192 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   return R3G_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair (cluster of 2 on one TPC) computes a 256 x 256 tile.  Each CTA stages
+// ITS 128 rows of X and ITS 128 of the 256 W rows (32 KB per k-block instead of 48 KB), the leader's single thread
+// issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, and each CTA's TMEM holds its own
+// 128 accumulator rows.  One third less L2 -> SMEM traffic per FLOP than the 128 x 256 single-CTA tile, which is
+// what bounds that kernel (12 TB/s of L2 bandwidth at 1.0 PFLOP/s), and room for a 6-deep ring.
+constexpr int kStages2 = 6;
+constexpr int kStageBytes2 = BM * BK * 2 + 128 * BK * 2;       // 16 KB of X + 16 KB of W per CTA
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+constexpr int BN2 = 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tmem_full_bar = empty_bar + kStages2;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (leader's copy is the one the MMA warp waits on)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;           // 256-row tiles here
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full_bar[s], 2);    // one arrival per CTA's producer (+ the transaction bytes of both)
+      mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kNumEpilogueWarps);  // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_base_smem);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int sg = tm / p.tiles_per_seg, l0 = (tm % p.tiles_per_seg) * 256 + (int)cta_rank * BM;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes2;
+          uint8_t* sb = sa + BM * BK * 2;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          tma_load_3d_2sm(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
+          tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, BN2, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
+            const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss_2sm(d_tmem, umma_desc_sw128(sa + k * 32, 1024, 16), umma_desc_sw128(sb + k * 32, 1024, 16), idesc,
+                          (kb | k) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int quad = warp & 3;
+    const int col_half = (warp - 2) >> 2;
+    const int row_in_tile = (int)cta_rank * BM + quad * 32 + lane;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int sg = tm / p.tiles_per_seg;
+      const int l = (tm % p.tiles_per_seg) * 256 + row_in_tile;
+      const bool row_ok = l < p.seg_len;
+      const int r = sg * p.seg_len + l;
+      const int64_t out_row = (int64_t)sg * p.y_seg_stride + l;
+      const __half* gate_row = p.gate ? p.gate + (int64_t)(row_ok ? r / p.gate_rows : 0) * p.gate_ld : nullptr;
+#pragma unroll 1
+      for (int c0 = col_half * (BN2 / 2); c0 < (col_half + 1) * (BN2 / 2); c0 += 32) {
+        const int n0 = tn * BN2 + c0;
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN2 + c0), v);
+        tmem_ld_wait();
+        if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA warp owns the wait
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
+  CUtensorMap tx, tw;
+  const int seg_len = a->seg_len > 0 ? a->seg_len : a->M;
+  const int nseg = a->M / seg_len;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)seg_len, (uint64_t)nseg};
+    const uint64_t strides[3] = {2, (uint64_t)a->ldx * 2, (uint64_t)(nseg > 1 ? a->x_seg_stride : seg_len) * a->ldx * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t strides[2] = {2, (uint64_t)a->K * 2};
+    const uint32_t box[2] = {BK, 128};
+    int rc = r3g_make_tmap_f16(ctx, &tw, a->w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  LinearParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = (const __half*)a->bias;
+  p.y = a->y; p.ldy = a->ldy;
+  p.seg_len = seg_len;
+  p.y_seg_stride = nseg > 1 ? a->y_seg_stride : seg_len;
+  p.tiles_per_seg = (seg_len + 255) / 256;
+  p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
+  p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
+  p.residual = a->residual_f32 ? nullptr : (const __half*)a->residual;
+  p.residual_f32 = a->residual_f32 ? (const float*)a->residual : nullptr;
+  p.ls_gamma = (const float*)a->ls_gamma;
+  p.out_f32 = a->out_f32;
+  p.tiles_m = nseg * p.tiles_per_seg;
+  p.tiles_n = a->N / BN2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  int clusters = ctx->num_sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  linear_kernel_2cta<<<2 * clusters, kNumThreads, kSmemBytes2, s>>>(tx, tw, p);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
 }  // namespace
 
 extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) {
@@ -363,6 +555,12 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
   // tile width: widest tile that still gives every SM work
   const int seg_len_ = a->seg_len > 0 ? a->seg_len : a->M;
   const int tiles_m = (a->M / seg_len_) * ((seg_len_ + BM - 1) / BM);
+  {
+    static int mode = -1;  // R3G_GEMM_2CTA=0 disables the CTA-pair kernel
+    if (mode < 0) { const char* e = getenv("R3G_GEMM_2CTA"); mode = (e && e[0] == '0') ? 0 : 1; }
+    const int64_t tiles2 = (int64_t)(a->M / seg_len_) * ((seg_len_ + 255) / 256) * (a->N / 256);
+    if (mode && a->N % 256 == 0 && tiles2 >= ctx->num_sms / 2) return launch_linear_2cta(ctx, a, s);
+  }
   if (a->N >= 256 && (int64_t)tiles_m * ((a->N + 255) / 256) >= ctx->num_sms) return launch_linear<256>(ctx, a, s);
   if (a->N >= 128) return launch_linear<128>(ctx, a, s);
   return launch_linear<64>(ctx, a, s);
