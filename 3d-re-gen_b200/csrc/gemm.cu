@@ -385,7 +385,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < kStages2; ++s) {
-      mbar_init(&full_bar[s], 2);    // one arrival per CTA's producer (+ the transaction bytes of both)
+      mbar_init(&full_bar[s], 1);    // the leader's expect_tx arrival; both CTAs' TMA bytes complete on it
       mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
@@ -412,8 +412,9 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes2;
           uint8_t* sb = sa + BM * BK * 2;
+          // the peer only issues its loads: its bytes are accounted on the leader's barrier (a phase cannot
+          // complete before they land because the leader armed it with the bytes of BOTH CTAs)
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
-          else mbar_arrive_cluster(&full_bar[stage], 0);
           tma_load_3d_2sm(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
           tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
           if (++stage == kStages2) { stage = 0; phase ^= 1; }

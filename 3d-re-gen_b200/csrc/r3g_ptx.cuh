@@ -193,11 +193,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
-// arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of the cluster
+// arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of the cluster.  RELAXED: the callers order
+// their TMEM accesses with tcgen05 fences; a .release.cluster arrive compiles to MEMBAR.ALL.GPU (microseconds).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {
