@@ -459,17 +459,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
       }
       const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+      bool waited_o = (j == 0);
       if (j == 0) {
         m_used = m_new;
       } else {
         const bool need = m_new - m_used > kRescaleThreshold;
-        // P buffer and O accumulator are both free once P_{j-1} V_{j-1} has completed
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
+          // rare: the O accumulator must be rescaled; P_{j-1} V_{j-1} has to have completed first
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+          waited_o = true;
           const float alpha = need ? ex2(m_used - m_new) : 1.f;
 #pragma unroll 1
-          for (int c = 0; c < kD; c += 8) {   // rare path: 8 columns at a time keeps the S row in registers
+          for (int c = 0; c < kD; c += 8) {   // 8 columns at a time keeps the S row in registers
             uint32_t o[8];
             tmem_ld8(tmem_addr(tmem_base, lane_base, kTmemO + c), o);
             tmem_ld_wait();
@@ -482,28 +484,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (need) m_used = m_new;
         }
       }
+      // probabilities for the whole row first (registers: the packed P row reuses the S row's registers) ...
       float rs = 0.f;
+      uint32_t pk[kBKV / 2];
 #pragma unroll
       for (int c = 0; c < kBKV; c += 16) {
-        uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2)
-          pk[i >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
-                                           fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
-        const uint32_t a01 = hadd2_u32(hadd2_u32(pk[0], pk[1]), hadd2_u32(pk[2], pk[3]));
-        const uint32_t a23 = hadd2_u32(hadd2_u32(pk[4], pk[5]), hadd2_u32(pk[6], pk[7]));
+          pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
+                                                 fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+        const uint32_t* q8 = &pk[c >> 1];
+        const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
+        const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
         const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
         rs += (f0.x + f0.y) + (f1.x + f1.y);
-        const uint32_t atom = p_row + (c >> 6) * (kBQ * 128);
-        const int u0 = (c & 63) >> 3;
+      }
+      // ... and only then wait for the previous P V to release the P tile: the exponentials above ran under it
+      if (!waited_o) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t addr = atom + (((u0 + q) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                       : "memory");
-        }
+      for (int c = 0; c < kBKV; c += 8) {
+        const uint32_t addr = p_row + (c >> 6) * (kBQ * 128) + (((((c & 63) >> 3)) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]), "r"(pk[(c >> 1) + 1]),
+                     "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
+                     : "memory");
       }
       l_run += rs;
       fence_proxy_async_smem();

@@ -553,16 +553,26 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
   if (a->ls_gamma && !a->residual_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: ls_gamma needs the fp32 residual form");
   if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
   cudaStream_t s = (cudaStream_t)stream;
-  // tile width: widest tile that still gives every SM work
+  // Tile choice: wave efficiency (tiles / (waves * units)) times a per-tile throughput factor measured on B200
+  // (CTA-pair 256x256: 1.08, 128x256: 1.0, 128x128: 0.9).  N = 1024 GEMMs with ~6k rows, for example, fill only
+  // 1.3 waves of 128x256 tiles but 2.6 waves of 128x128 tiles.
   const int seg_len_ = a->seg_len > 0 ? a->seg_len : a->M;
-  const int tiles_m = (a->M / seg_len_) * ((seg_len_ + BM - 1) / BM);
-  {
-    static int mode = -1;  // R3G_GEMM_2CTA=0 disables the CTA-pair kernel
-    if (mode < 0) { const char* e = getenv("R3G_GEMM_2CTA"); mode = (e && e[0] == '0') ? 0 : 1; }
-    const int64_t tiles2 = (int64_t)(a->M / seg_len_) * ((seg_len_ + 255) / 256) * (a->N / 256);
-    if (mode && a->N % 256 == 0 && tiles2 >= ctx->num_sms / 2) return launch_linear_2cta(ctx, a, s);
-  }
-  if (a->N >= 256 && (int64_t)tiles_m * ((a->N + 255) / 256) >= ctx->num_sms) return launch_linear<256>(ctx, a, s);
+  const int nseg_ = a->M / seg_len_;
+  const int sms = ctx->num_sms;
+  auto eff = [&](int64_t tiles, int units, double factor) {
+    if (tiles <= 0) return 0.0;
+    const int64_t waves = (tiles + units - 1) / units;
+    return factor * (double)tiles / (double)(waves * units);
+  };
+  static int mode = -1;  // R3G_GEMM_2CTA=0 disables the CTA-pair kernel
+  if (mode < 0) { const char* e = getenv("R3G_GEMM_2CTA"); mode = (e && e[0] == '0') ? 0 : 1; }
+  const int64_t tm128 = (int64_t)nseg_ * ((seg_len_ + 127) / 128), tm256 = (int64_t)nseg_ * ((seg_len_ + 255) / 256);
+  // measured: the CTA-pair tile wins for short K (epilogue-heavy), the single-CTA tile for K >= 4096
+  const double e2 = (mode && a->N % 256 == 0) ? eff(tm256 * (a->N / 256), sms / 2, a->K <= 2048 ? 1.08 : 0.93) : 0.0;
+  const double e256 = a->N >= 256 ? eff(tm128 * ((a->N + 255) / 256), sms, 1.0) : 0.0;
+  const double e128 = a->N >= 128 ? eff(tm128 * ((a->N + 127) / 128), sms, 0.9) : 0.0;
+  if (e2 > 0.0 && e2 >= e256 && e2 >= e128) return launch_linear_2cta(ctx, a, s);
+  if (e256 > 0.0 && e256 >= e128) return launch_linear<256>(ctx, a, s);
   if (a->N >= 128) return launch_linear<128>(ctx, a, s);
   return launch_linear<64>(ctx, a, s);
 }
