@@ -107,15 +107,15 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
         }
       }
     }
-    if (p.act && n0 < p.act_col1 && n0 + 32 > p.act_col0) {
+    // act_col0 / act_col1 are multiples of 32 (checked at the API), so a 32-column chunk is activated as a whole:
+    // one warp-uniform branch, then 32 independent element chains (per-element range checks serialise the MUFU chains)
+    if (p.act && n0 >= p.act_col0 && n0 < p.act_col1) {
+      if (p.act == 1) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + j;
-        if (n >= p.act_col0 && n < p.act_col1) {
-          // the reference's Linear output is fp16 before the activation sees it
-          const float xh = __half2float(__float2half_rn(f[j]));
-          f[j] = (p.act == 1) ? gelu_tanh_f(xh) : gelu_erf_f(xh);
-        }
+        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_f(__half2float(__float2half_rn(f[j])));  // Linear output is fp16
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(__half2float(__float2half_rn(f[j])));
       }
     }
     if (p.residual) {
@@ -552,9 +552,11 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
     return r3g_fail(ctx, R3G_E_INVALID, "linear: an fp32 output takes an fp32 residual (residual_f32=1) and vice versa");
   if (a->ls_gamma && !a->residual_f32) return r3g_fail(ctx, R3G_E_INVALID, "linear: ls_gamma needs the fp32 residual form");
   if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
+  if (a->act && (a->act_col0 % 32 || a->act_col1 % 32))
+    return r3g_fail(ctx, R3G_E_INVALID, "linear: activation column range must be aligned to 32 columns");
   cudaStream_t s = (cudaStream_t)stream;
   // Tile choice: wave efficiency (tiles / (waves * units)) times a per-tile throughput factor measured on B200
-  // (CTA-pair 256x256: 1.08, 128x256: 1.0, 128x128: 0.9).  N = 1024 GEMMs with ~6k rows, for example, fill only
+  // (CTA-pair 256x256: 1.08 for K <= 2048 else 0.93, 128x256: 1.0, 128x128: 0.7).  N = 1024 GEMMs with ~6k rows, for example, fill only
   // 1.3 waves of 128x256 tiles but 2.6 waves of 128x128 tiles.
   const int seg_len_ = a->seg_len > 0 ? a->seg_len : a->M;
   const int nseg_ = a->M / seg_len_;
@@ -570,7 +572,7 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
   // measured: the CTA-pair tile wins for short K (epilogue-heavy), the single-CTA tile for K >= 4096
   const double e2 = (mode && a->N % 256 == 0) ? eff(tm256 * (a->N / 256), sms / 2, a->K <= 2048 ? 1.08 : 0.93) : 0.0;
   const double e256 = a->N >= 256 ? eff(tm128 * ((a->N + 255) / 256), sms, 1.0) : 0.0;
-  const double e128 = a->N >= 128 ? eff(tm128 * ((a->N + 127) / 128), sms, 0.9) : 0.0;
+  const double e128 = a->N >= 128 ? eff(tm128 * ((a->N + 127) / 128), sms, 0.7) : 0.0;
   if (e2 > 0.0 && e2 >= e256 && e2 >= e128) return launch_linear_2cta(ctx, a, s);
   if (e256 > 0.0 && e256 >= e128) return launch_linear<256>(ctx, a, s);
   if (a->N >= 128) return launch_linear<128>(ctx, a, s);

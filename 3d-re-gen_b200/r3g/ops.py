@@ -1,6 +1,8 @@
 """Torch-tensor front end of the C ABI (include/r3g.h).  Torch is plumbing only: it owns device memory
 and the stream; every computation below happens in libr3g.so.  No fallback paths."""
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -302,6 +304,18 @@ class MarchingCubesError(RuntimeError):
     pass
 
 
+_MC_WS = {}
+
+
+def _mc_workspace(device, nbytes):
+    """One cached marching-cubes workspace per device (272 MB at 257^3): not re-requested from the allocator per object."""
+    ws = _MC_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _MC_WS[device] = ws
+    return ws
+
+
 def marching_cubes(grid, level=0.0, bounds=None):
     """grid: CUDA float32 [n0,n1,n2].  Returns (verts float32 [V,3], faces int32 [F,3]) CUDA tensors in
     skimage's output convention.  Raises ValueError / RuntimeError like skimage.measure.marching_cubes."""
@@ -311,7 +325,13 @@ def marching_cubes(grid, level=0.0, bounds=None):
     ctx = _ctx(grid)
     n0, n1, n2 = grid.shape
     ws_bytes = ctx.lib.r3g_mc_workspace_bytes(n0, n1, n2)
-    ws = torch.empty(ws_bytes, device=grid.device, dtype=torch.uint8)
+    dbg = os.environ.get("R3G_DEBUG_TIMING") == "1"
+    if dbg:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+    ws = _mc_workspace(grid.device, ws_bytes)
+    if dbg:
+        t1 = time.perf_counter()
     nv, nf = C.c_int64(0), C.c_int64(0)
     rc = ctx.lib.r3g_mc_count(ctx.handle, _p(grid), n0, n1, n2, float(level), _p(ws), ws_bytes, C.byref(nv),
                               C.byref(nf), _stream())
@@ -320,14 +340,23 @@ def marching_cubes(grid, level=0.0, bounds=None):
     if rc == _abi.R3G_E_NOSURFACE:
         raise RuntimeError("No surface found at the given iso value.")
     ctx.check(rc)
+    if dbg:
+        t2 = time.perf_counter()
     verts = torch.empty(nv.value, 3, device=grid.device, dtype=torch.float32)
     faces = torch.empty(nf.value, 3, device=grid.device, dtype=torch.int32)
+    if dbg:
+        t3 = time.perf_counter()
     bptr = C.c_void_p(0)
     if bounds is not None:
         barr = (C.c_double * 6)(*[float(v) for v in bounds])
         bptr = C.cast(barr, C.c_void_p)
     ctx.check(ctx.lib.r3g_mc_extract(ctx.handle, _p(grid), n0, n1, n2, float(level), bptr, _p(ws), ws_bytes,
                                      _p(verts), _p(faces), _stream()))
+    if dbg:
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        print(f"[r3g mc] ws {1e3 * (t1 - t0):.2f} ms, count {1e3 * (t2 - t1):.2f} ms, alloc {1e3 * (t3 - t2):.2f} ms, "
+              f"extract {1e3 * (t4 - t3):.2f} ms, V={nv.value} F={nf.value}", flush=True)
     return verts, faces
 
 
