@@ -549,6 +549,264 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v3 = v2 with TWO threads per query row (8 softmax warps per CTA, 16 per SM): warp w and warp w+4 own the same 32
+// TMEM lanes and split the 128 score columns (and the 64 output columns) in halves.  Twice the warps per scheduler
+// hide the MUFU / TMEM latencies that left v2's exponent pipe half idle.  The two threads of a row exchange their
+// partial row maximum (every tile) and partial row sum (once, at the end) through spare TMEM columns -- there is no
+// shared memory left (2 CTAs x 113 KB) -- and meet on a 64-thread named barrier per warp pair.
+constexpr int kThreadsV3 = 320;           // warps 0..7 softmax, warp 8 TMA, warp 9 MMA
+constexpr uint32_t kTmemX = 192;          // exchange columns: [kTmemX + 2*parity + half]
+
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pair_barrier(int quad) {
+  asm volatile("bar.sync %0, 64;\n" ::"r"(quad + 1) : "memory");
+}
+// publish `mine` to the partner thread of this row and fetch its value
+__device__ __forceinline__ float pair_exchange(uint32_t tmem_base, uint32_t lane_base, int quad, int half, int slot,
+                                               float mine) {
+  tmem_st1(tmem_addr(tmem_base, lane_base, kTmemX + 2 * slot + half), __float_as_uint(mine));
+  tmem_st_wait();
+  tc_fence_before();
+  pair_barrier(quad);
+  tc_fence_after();
+  const uint32_t other = tmem_ld1(tmem_addr(tmem_base, lane_base, kTmemX + 2 * slot + (half ^ 1)));
+  tmem_ld_wait();
+  return __uint_as_float(other);
+}
+
+__global__ void __launch_bounds__(kThreadsV3, 2)
+attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
+  const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
+  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kTileBytes;
+  uint8_t* sP = sV + kKVStages * kTileBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* v_full = k_full + kKVStages;
+  uint64_t* k_empty = v_full + kKVStages;
+  uint64_t* v_empty = k_empty + kKVStages;
+  uint64_t* s_full = v_empty + kKVStages;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_free + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + kBKV - 1) / kBKV;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<kTmemCols>(tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        tma_load_4d(sV + st * kTileBytes, &tmap_v, &v_full[st], 0, j * kBKV, h, b, kEvictLast);
+      }
+    }
+  } else if (warp == 9) {
+    constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);
+    const uint32_t aq = smem_u32(sQ);
+    auto issue_s = [&](int j) {
+      const int st = j % kKVStages;
+      mbar_wait(&k_full[st], (j / kKVStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ak = smem_u32(sK + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem_base + kTmemS, umma_desc_sw128(aq + k * 32, 1024, 16), umma_desc_sw128(ak + k * 32, 1024, 16),
+                  idesc_s, k ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(s_free, j & 1);
+        issue_s(j + 1);
+      }
+      const int st = j % kKVStages;
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[st], (j / kKVStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBKV / 16; ++k)
+          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
+                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32);
+    constexpr int kHalf = kBKV / 2;                      // 64 score columns per thread
+    float m_used = -INFINITY, l_part = 0.f;
+    // this thread's P columns are exactly one 128-byte swizzle atom row
+    const uint32_t p_row = smem_u32(sP) + half * (kBQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = min(kBKV, p.Lk - j * kBKV) - half * kHalf;   // valid columns among this thread's 64
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t s[kHalf];
+      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + half * kHalf), &s[0]);
+      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + half * kHalf + 32), &s[32]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      if (valid < kHalf) {
+#pragma unroll
+        for (int i = 0; i < kHalf; ++i)
+          if (i >= valid) s[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kHalf; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      }
+      const float mine = fmaxf(mx0, mx1);
+      const float m_new = fmaxf(mine, pair_exchange(tmem_base, lane_base, quad, half, j & 1, mine)) * p.scale_log2;
+      bool waited_o = (j == 0);
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = m_new - m_used > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {   // same rows, same m_new in both warps of the pair: same decision
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+          waited_o = true;
+          const float alpha = need ? ex2(m_used - m_new) : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < kD / 2; c += 8) {
+            uint32_t o[8];
+            tmem_ld8(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2) + c), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st8(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2) + c), o);
+          }
+          tmem_st_wait();
+          l_part *= alpha;
+          if (need) m_used = m_new;
+        }
+      }
+      float rs = 0.f;
+      uint32_t pk[kHalf / 2];
+#pragma unroll
+      for (int c = 0; c < kHalf; c += 16) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
+                                                 fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+        const uint32_t* q8 = &pk[c >> 1];
+        const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
+        const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
+        rs += (f0.x + f0.y) + (f1.x + f1.y);
+      }
+      l_part += rs;
+      if (!waited_o) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < kHalf; c += 8) {
+        const uint32_t addr = p_row + ((((c >> 3)) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]), "r"(pk[(c >> 1) + 1]),
+                     "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float l_tot = l_part + pair_exchange(tmem_base, lane_base, quad, half, n_kv & 1, l_part);
+    const float inv_l = 1.f / l_tot;
+    const int qrow = q0 + row;
+    __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl + half * (kD / 2);
+    uint32_t v[32];
+    tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2)), v);
+    tmem_ld_wait();
+    if (qrow < p.Lq) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o4;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ow[i] = pack_half2(__uint_as_float(v[8 * q + 2 * i]) * inv_l, __uint_as_float(v[8 * q + 2 * i + 1]) * inv_l);
+        *reinterpret_cast<uint4*>(op + 8 * q) = o4;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
                  int L) {
   const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)L, (uint64_t)H, (uint64_t)B};
@@ -578,9 +836,15 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
   static bool use_v1 = false;
+  static int version = 3;   // R3G_ATTN=1|2|3 selects the kernel generation (parity tests run all of them)
   if (!attr_set) {
     const char* e = getenv("R3G_ATTN_V1");
     use_v1 = e && e[0] == '1';
+    const char* ev = getenv("R3G_ATTN");
+    if (ev && ev[0] >= '1' && ev[0] <= '3') version = ev[0] - '0';
+    if (use_v1) version = 1;
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v3, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -588,10 +852,12 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
     attr_set = true;
   }
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->H, a->B);
-  if (use_v1)
+  if (version == 1)
     attention_kernel_v1<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
-  else
+  else if (version == 2)
     attention_kernel<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  else
+    attention_kernel_v3<<<grid, kThreadsV3, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
