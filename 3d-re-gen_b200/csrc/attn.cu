@@ -556,6 +556,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // partial row maximum (every tile) and partial row sum (once, at the end) through spare TMEM columns -- there is no
 // shared memory left (2 CTAs x 113 KB) -- and meet on a 64-thread named barrier per warp pair.
 constexpr int kThreadsV3 = 320;           // warps 0..7 softmax, warp 8 TMA, warp 9 MMA
+constexpr int kPolyEvery = 4;             // every kPolyEvery-th pair of exponentials runs on the FMA pipe (0 = none)
+
+// 2^x on the FMA pipe: Cody-Waite split with the 1.5*2^23 rounding constant, cubic for 2^f on [-0.5, 0.5]
+// (max relative error 1.0e-4 < fp16 rounding), exponent re-inserted with one integer multiply-add.
+// 1 ALU + 6 FMA-pipe instructions instead of one MUFU.EX2: the exp unit (16 lanes/clk/SM) is what bounds this kernel.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -30.f);                                   // masked columns (-inf) -> 2^-30 -> 0 in fp16
+  const float t = x + 12582912.f;                        // integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float pl = fmaf(0.0550081f, f, 0.24220917f);
+  pl = fmaf(pl, f, 0.69328282f);
+  pl = fmaf(pl, f, 1.0f);
+  return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(pl));   // (bits(t) << 23) + bits(p)
+}
 constexpr uint32_t kTmemX = 192;          // exchange columns: [kTmemX + 2*parity + half]
 
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
@@ -751,9 +765,14 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
       for (int c = 0; c < kHalf; c += 16) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2)
-          pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
-                                                 fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+        for (int i = 0; i < 16; i += 2) {
+          const float x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
+          const float x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
+          if (kPolyEvery > 0 && ((i >> 1) % kPolyEvery) == kPolyEvery - 1)
+            pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
+          else
+            pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(x0, x1));
+        }
         const uint32_t* q8 = &pk[c >> 1];
         const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
         const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));

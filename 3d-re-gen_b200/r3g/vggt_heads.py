@@ -1,0 +1,206 @@
+"""VGGT camera head, DPT depth head and pose utilities -- the remaining call surface of stage 4
+(src/camera_and_pointcloud/minimal_demo_vggt.py:305-321):
+
+    pose_enc = model.camera_head(tokens)[-1]                       vggt/heads/camera_head.py:73-141
+    extrinsic, intrinsic = pose_encoding_to_extri_intri(pose_enc, (H, W))   vggt/utils/pose_enc.py:62-124
+    depth, conf = model.depth_head(tokens, images=images, patch_start_idx=ps_idx)   vggt/heads/dpt_head.py:115-291
+
+These heads run OUTSIDE autocast in fp32 in the reference and are small next to the aggregator (camera head:
+S tokens only; DPT: ~0.4 TFLOP of cuDNN convolutions per frame).  They are expressed here with torch operators
+(library convolutions, as in the reference) on the reference's state_dict keys; moving them to r3g kernels is a
+"next" row.  Functional style: weights live in a dict, nothing is an nn.Module.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def quat_to_mat(q):
+    """vggt/utils/rotation.py:14-44 -- scalar-last quaternion, un-normalised input allowed."""
+    i, j, k, r = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    m = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return m.reshape(q.shape[:-1] + (3, 3))
+
+
+def pose_encoding_to_extri_intri(pose_encoding, image_size_hw=None, pose_encoding_type="absT_quaR_FoV",
+                                 build_intrinsics=True):
+    if pose_encoding_type != "absT_quaR_FoV":
+        raise NotImplementedError
+    T, quat = pose_encoding[..., :3], pose_encoding[..., 3:7]
+    extrinsics = torch.cat([quat_to_mat(quat), T[..., None]], dim=-1)
+    intrinsics = None
+    if build_intrinsics:
+        H, W = image_size_hw
+        fy = (H / 2.0) / torch.tan(pose_encoding[..., 7] / 2.0)
+        fx = (W / 2.0) / torch.tan(pose_encoding[..., 8] / 2.0)
+        intrinsics = torch.zeros(pose_encoding.shape[:2] + (3, 3), device=pose_encoding.device)
+        intrinsics[..., 0, 0], intrinsics[..., 1, 1] = fx, fy
+        intrinsics[..., 0, 2], intrinsics[..., 1, 2], intrinsics[..., 2, 2] = W / 2, H / 2, 1.0
+    return extrinsics, intrinsics
+
+
+def _ln(sd, name, x, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+def _lin(sd, name, x):
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _trunk_block(sd, p, x, heads):
+    """vggt/layers/block.py Block without qk-norm / RoPE (camera trunk: dim 2048, 16 heads of 128)."""
+    B, N, C = x.shape
+    qkv = _lin(sd, p + "attn.qkv", _ln(sd, p + "norm1", x)).reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(B, N, C)
+    x = x + sd[p + "ls1.gamma"] * _lin(sd, p + "attn.proj", o)
+    h = _lin(sd, p + "mlp.fc2", F.gelu(_lin(sd, p + "mlp.fc1", _ln(sd, p + "norm2", x))))
+    return x + sd[p + "ls2.gamma"] * h
+
+
+class CameraHead:
+    def __init__(self, sd, prefix="camera_head.", trunk_depth=4, num_heads=16, device="cuda"):
+        self.sd = {k[len(prefix):]: v.detach().to(device=device, dtype=torch.float32) for k, v in sd.items()
+                   if k.startswith(prefix)}
+        self.trunk_depth, self.heads = trunk_depth, num_heads
+
+    @torch.no_grad()
+    def __call__(self, aggregated_tokens_list, num_iterations=4):
+        sd = self.sd
+        pose_tokens = _ln(sd, "token_norm", aggregated_tokens_list[-1][:, :, 0].float())
+        B, S, C = pose_tokens.shape
+        pred, outs = None, []
+        for _ in range(num_iterations):
+            inp = sd["empty_pose_tokens"].expand(B, S, -1) if pred is None else pred
+            mod = _lin(sd, "poseLN_modulation.1", F.silu(_lin(sd, "embed_pose", inp)))
+            shift, scale, gate = mod.chunk(3, dim=-1)
+            x = gate * (F.layer_norm(pose_tokens, (C,), eps=1e-6) * (1 + scale) + shift) + pose_tokens
+            for i in range(self.trunk_depth):
+                x = _trunk_block(sd, f"trunk.{i}.", x, self.heads)
+            delta = _lin(sd, "pose_branch.fc2", F.gelu(_lin(sd, "pose_branch.fc1", _ln(sd, "trunk_norm", x))))
+            pred = delta if pred is None else pred + delta
+            # activate_pose: translation linear, quaternion linear, field of view relu (head_act.py:12-35)
+            outs.append(torch.cat([pred[..., :3], pred[..., 3:7], F.relu(pred[..., 7:])], dim=-1))
+        return outs
+
+
+def _uv_embed(x, W, H, ratio=0.1):
+    """_apply_pos_embed (dpt_head.py:249-259) with create_uv_grid / position_grid_to_embed (heads/utils.py)."""
+    pw, ph, C = x.shape[-1], x.shape[-2], x.shape[1]
+    aspect = W / H
+    diag = (aspect ** 2 + 1.0) ** 0.5
+    sx, sy = aspect / diag, 1.0 / diag
+    xs = torch.linspace(-sx * (pw - 1) / pw, sx * (pw - 1) / pw, steps=pw, dtype=x.dtype, device=x.device)
+    ys = torch.linspace(-sy * (ph - 1) / ph, sy * (ph - 1) / ph, steps=ph, dtype=x.dtype, device=x.device)
+    uu, vv = torch.meshgrid(xs, ys, indexing="xy")
+    pos = torch.stack((uu, vv), -1).reshape(-1, 2)
+
+    def sincos(d, p):
+        omega = torch.arange(d // 2, dtype=torch.double, device=x.device) / (d / 2.0)
+        out = torch.einsum("m,d->md", p, 1.0 / 100 ** omega)
+        return torch.cat([out.sin(), out.cos()], 1).float()
+
+    emb = torch.cat([sincos(C // 2, pos[:, 0]), sincos(C // 2, pos[:, 1])], -1).view(ph, pw, C)
+    return x + (emb * ratio).permute(2, 0, 1)[None]
+
+
+class DPTHead:
+    def __init__(self, sd, prefix="depth_head.", patch_size=14, activation="exp", conf_activation="expp1",
+                 intermediate_layer_idx=(4, 11, 17, 23), pos_embed=True, device="cuda"):
+        self.sd = {k[len(prefix):]: v.detach().to(device=device, dtype=torch.float32) for k, v in sd.items()
+                   if k.startswith(prefix)}
+        self.patch_size, self.activation, self.conf_activation = patch_size, activation, conf_activation
+        self.layers, self.pos_embed = tuple(intermediate_layer_idx), pos_embed
+
+    def _conv(self, name, x, **kw):
+        return F.conv2d(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), **kw)
+
+    def _rcu(self, p, x):
+        """ResidualConvUnit (dpt_head.py:344-392).  The reference's activation is nn.ReLU(inplace=True), so its
+        `activation(x)` overwrites x and the skip connection adds relu(x), not x -- replicated."""
+        xr = F.relu(x)
+        out = self._conv(p + "conv1", xr, padding=1)
+        return self._conv(p + "conv2", F.relu(out), padding=1) + xr
+
+    def _fuse(self, p, x, skip=None, size=None):
+        if skip is not None:
+            x = x + self._rcu(p + "resConfUnit1.", skip)
+        x = self._rcu(p + "resConfUnit2.", x)
+        kw = dict(size=size) if size is not None else dict(scale_factor=2)
+        x = F.interpolate(x, **kw, mode="bilinear", align_corners=True)
+        return self._conv(p + "out_conv", x)
+
+    @torch.no_grad()
+    def __call__(self, aggregated_tokens_list, images, patch_start_idx, frames_chunk_size=8):
+        B, S, _, H, W = images.shape
+        if frames_chunk_size is None or frames_chunk_size >= S:
+            return self._impl(aggregated_tokens_list, H, W, B, S, patch_start_idx, 0, S)
+        preds, confs = [], []
+        for s0 in range(0, S, frames_chunk_size):
+            pr, cf = self._impl(aggregated_tokens_list, H, W, B, S, patch_start_idx, s0, min(s0 + frames_chunk_size, S))
+            preds.append(pr)
+            confs.append(cf)
+        return torch.cat(preds, 1), torch.cat(confs, 1)
+
+    def _impl(self, tokens, H, W, B, S_all, psi, s0, s1):
+        sd, S = self.sd, s1 - s0
+        ph, pw = H // self.patch_size, W // self.patch_size
+        feats = []
+        for d, layer in enumerate(self.layers):
+            x = tokens[layer][:, s0:s1, psi:].float().reshape(B * S, ph * pw, -1)
+            x = _ln(sd, "norm", x).permute(0, 2, 1).reshape(B * S, -1, ph, pw)
+            x = self._conv(f"projects.{d}", x)
+            if self.pos_embed:
+                x = _uv_embed(x, W, H)
+            if d == 0:
+                x = F.conv_transpose2d(x, sd["resize_layers.0.weight"], sd["resize_layers.0.bias"], stride=4)
+            elif d == 1:
+                x = F.conv_transpose2d(x, sd["resize_layers.1.weight"], sd["resize_layers.1.bias"], stride=2)
+            elif d == 3:
+                x = self._conv("resize_layers.3", x, stride=2, padding=1)
+            feats.append(x)
+        l1, l2, l3, l4 = (self._conv(f"scratch.layer{i + 1}_rn", f, padding=1) for i, f in enumerate(feats))
+        out = self._fuse("scratch.refinenet4.", l4, None, size=l3.shape[2:])
+        out = self._fuse("scratch.refinenet3.", out, l3, size=l2.shape[2:])
+        out = self._fuse("scratch.refinenet2.", out, l2, size=l1.shape[2:])
+        out = self._fuse("scratch.refinenet1.", out, l1)
+        out = self._conv("scratch.output_conv1", out, padding=1)
+        out = F.interpolate(out, size=(ph * self.patch_size, pw * self.patch_size), mode="bilinear", align_corners=True)
+        if self.pos_embed:
+            out = _uv_embed(out, W, H)
+        out = self._conv("scratch.output_conv2.2", F.relu(self._conv("scratch.output_conv2.0", out, padding=1)))
+        fmap = out.permute(0, 2, 3, 1)
+        xyz, conf = fmap[..., :-1], fmap[..., -1]
+        if self.activation == "exp":
+            pts = torch.exp(xyz)
+        elif self.activation == "inv_log":
+            pts = torch.sign(xyz) * torch.expm1(torch.abs(xyz))
+        else:
+            raise ValueError(f"Unknown activation: {self.activation}")
+        cf = 1 + conf.exp() if self.conf_activation == "expp1" else conf.exp()
+        return pts.view(B, S, *pts.shape[1:]), cf.view(B, S, *cf.shape[1:])
+
+
+class VGGT:
+    """`model.aggregator / model.camera_head / model.depth_head`, as the stage script uses the reference's VGGT."""
+
+    def __init__(self, img_size=518, patch_size=14, embed_dim=1024, device="cuda", **agg_kwargs):
+        from .vggt import Aggregator
+        self.device = torch.device(device)
+        self.aggregator = Aggregator(img_size=img_size, patch_size=patch_size, embed_dim=embed_dim, device=device,
+                                     **agg_kwargs)
+        self.camera_head = self.depth_head = None
+        self.patch_size = patch_size
+
+    def load_state_dict(self, sd, strict=True):
+        self.aggregator.load_state_dict(sd, prefix="aggregator.")
+        self.camera_head = CameraHead(sd, device=self.device)
+        self.depth_head = DPTHead(sd, patch_size=self.patch_size, device=self.device)
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self

@@ -97,3 +97,42 @@ def test_vggt_restatement_matches_reference_fixture(golden_dir):
     for tag in ("native", "interp"):
         y = V.dino_patch_tokens(vsd, "", torch.from_numpy(z[f"vit_x_{tag}"]), 2, 2, 14, 4)
         np.testing.assert_allclose(y.numpy(), z[f"vit_y_{tag}"], rtol=0, atol=3e-5)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_vggt_heads_mirror_matches_reference_modules_live():
+    """The torch-operator mirrors of CameraHead / DPTHead / pose utilities against the reference modules (CPU, fp32)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3d-re-gen_b200"))
+    ref_import.vggt_package()
+    from vggt.heads.camera_head import CameraHead as RefCam
+    from vggt.heads.dpt_head import DPTHead as RefDPT
+    from vggt.utils.pose_enc import pose_encoding_to_extri_intri as ref_pose
+    from r3g import vggt_heads as M
+    torch.manual_seed(0)
+    C, S, H, W = 128, 2, 56, 70
+    ph, pw = H // 14, W // 14
+    toks = [torch.randn(1, S, 5 + ph * pw, C) for _ in range(4)]
+    cam = RefCam(dim_in=C, trunk_depth=2, num_heads=2).eval()
+    with torch.no_grad():
+        for n, p in cam.named_parameters():
+            if "gamma" in n or n == "empty_pose_tokens":
+                p.copy_(0.3 * torch.randn_like(p))
+        ref = cam(toks)
+    mine = M.CameraHead({"camera_head." + k: v for k, v in cam.state_dict().items()}, trunk_depth=2, num_heads=2,
+                        device="cpu")(toks)
+    for a, b in zip(mine, ref):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=0, atol=2e-5)
+    e1, k1 = M.pose_encoding_to_extri_intri(mine[-1], (H, W))
+    e2, k2 = ref_pose(ref[-1], (H, W))
+    np.testing.assert_allclose(e1.numpy(), e2.numpy(), atol=1e-5)
+    np.testing.assert_allclose(k1.numpy(), k2.numpy(), rtol=1e-5)
+    dpt = RefDPT(dim_in=C, output_dim=2, activation="exp", conf_activation="expp1", features=32,
+                 out_channels=[16, 32, 64, 64], intermediate_layer_idx=[0, 1, 2, 3]).eval()
+    imgs = torch.rand(1, S, 3, H, W)
+    with torch.no_grad():
+        rd, rc = dpt(toks, images=imgs, patch_start_idx=5)
+    md, mc = M.DPTHead({"depth_head." + k: v for k, v in dpt.state_dict().items()}, intermediate_layer_idx=(0, 1, 2, 3),
+                       device="cpu")(toks, imgs, 5)
+    np.testing.assert_allclose(md.numpy(), rd.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(mc.numpy(), rc.numpy(), rtol=1e-4, atol=1e-5)
