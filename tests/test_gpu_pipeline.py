@@ -65,21 +65,3 @@ def test_surface_extractor_swallows_failures_like_the_reference():
     ex = MCSurfaceExtractor()
     flat = torch.zeros(1, 9, 9, 9, device="cuda")
     assert ex(flat, mc_level=0.0, bounds=1.01, octree_resolution=8) == [None]
-
-
-def test_simple_mesh_glb_roundtrip(tmp_path):
-    import json
-    import struct
-    from r3g.pipelines import SimpleMesh
-    v = np.random.rand(5, 3).astype(np.float32)
-    f = np.array([[0, 1, 2], [2, 3, 4]], np.int32)
-    p = SimpleMesh(v, f).export(str(tmp_path / "a.glb"))
-    raw = open(p, "rb").read()
-    magic, ver, total = struct.unpack("<4sII", raw[:12])
-    assert magic == b"glTF" and ver == 2 and total == len(raw)
-    jl = struct.unpack("<I", raw[12:16])[0]
-    doc = json.loads(raw[20:20 + jl])
-    off = 20 + jl + 8
-    idx = np.frombuffer(raw[off:off + 24], "<u4").reshape(2, 3)
-    pos = np.frombuffer(raw[off + 24:off + 24 + 60], "<f4").reshape(5, 3)
-    assert np.array_equal(idx, f) and np.array_equal(pos, v) and doc["accessors"][1]["count"] == 5

@@ -1,0 +1,79 @@
+"""CPU: host-side logic of the pipeline mirror that needs no GPU (mesh export, scheduler mirror, image processor,
+stage-script helpers)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_simple_mesh_glb_roundtrip(tmp_path):
+    import json
+    import struct
+    from r3g.pipelines import SimpleMesh
+    v = np.random.rand(5, 3).astype(np.float32)
+    f = np.array([[0, 1, 2], [2, 3, 4]], np.int32)
+    p = SimpleMesh(v, f).export(str(tmp_path / "a.glb"))
+    raw = open(p, "rb").read()
+    magic, ver, total = struct.unpack("<4sII", raw[:12])
+    assert magic == b"glTF" and ver == 2 and total == len(raw)
+    jl = struct.unpack("<I", raw[12:16])[0]
+    doc = json.loads(raw[20:20 + jl])
+    off = 20 + jl + 8
+    idx = np.frombuffer(raw[off:off + 24], "<u4").reshape(2, 3)
+    pos = np.frombuffer(raw[off + 24:off + 24 + 60], "<f4").reshape(5, 3)
+    assert np.array_equal(idx, f) and np.array_equal(pos, v) and doc["accessors"][1]["count"] == 5
+
+
+def test_scheduler_mirror_matches_reference_fixture(golden_dir):
+    from r3g.scheduler import FlowMatchEulerDiscreteScheduler
+    z = np.load(os.path.join(golden_dir, "scheduler.npz"))
+    sch = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000)
+    for n in (1, 5, 50):
+        sch.set_timesteps(sigmas=np.linspace(0, 1, n))
+        assert np.array_equal(sch.timesteps.numpy(), z[f"timesteps_{n}"])
+        assert np.array_equal(sch.sigmas.numpy(), z[f"sigmas_{n}"])
+    sch.set_timesteps(sigmas=np.linspace(0, 1, 5))
+    x = torch.from_numpy(z["euler_x"][0])
+    for i, t in enumerate(sch.timesteps[:3]):
+        x = sch.step(torch.from_numpy(z["euler_v"][i]), t, x).prev_sample
+        assert np.array_equal(x.numpy(), z["euler_x"][i + 1])
+    with pytest.raises(ValueError):
+        sch.step(torch.zeros(1), 3, torch.zeros(1))
+
+
+def test_image_processor_against_reference_when_available():
+    import ref_import
+    if not ref_import.available():
+        pytest.skip("/root/reference not present")
+    from PIL import Image
+    from r3g.preprocessors import ImageProcessorV2
+    ref = ref_import.hunyuan_preprocessors().ImageProcessorV2(size=512, border_ratio=0.15)
+    rng = np.random.default_rng(0)
+    rgba = np.zeros((300, 420, 4), np.uint8)
+    rgba[..., :3] = rng.integers(0, 256, (300, 420, 3))
+    yy, xx = np.mgrid[0:300, 0:420]
+    rgba[..., 3] = ((((xx - 200) / 120) ** 2 + ((yy - 160) / 90) ** 2) <= 1) * 255
+    img = Image.fromarray(rgba, "RGBA")
+    a, b = ImageProcessorV2(512, 0.15)(img), ref(img)
+    assert torch.equal(a["image"], b["image"]) and torch.equal(a["mask"], b["mask"])
+    assert a["image"].shape == (1, 3, 512, 512) and a["mask"].shape == (1, 1, 512, 512)
+
+
+def test_stage3_twin_file_contract(tmp_path, monkeypatch):
+    """The stage-3 twin's host helpers: config loading, name filter, output clearing (no GPU work here)."""
+    sys.path.insert(0, os.path.join(ROOT, "stages", "2d_to_3d_models"))
+    import importlib
+    run = importlib.import_module("run")
+    d = tmp_path / "out"
+    (d / "old").mkdir(parents=True)
+    (d / "old" / "x.glb").write_bytes(b"1")
+    (d / "stale.txt").write_text("x")
+    run.clear_output_directory(str(d))
+    assert os.listdir(d) == []
+    cfg = tmp_path / "c.yaml"
+    cfg.write_text("num_inf_steps_hy: 50\noctree_resolution_hy: 256\nuse_banana: false\n")
+    assert run.load_config(str(cfg))["octree_resolution_hy"] == 256
