@@ -319,10 +319,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
+// 2^x on the FMA pipe: Cody-Waite split with the 1.5*2^23 rounding constant, cubic for 2^f on [-0.5, 0.5]
+// (max relative error 1.0e-4 < fp16 rounding), exponent re-inserted with one integer multiply-add.
+// 1 ALU + 6 FMA-pipe instructions instead of one MUFU.EX2: the exp unit (16 lanes/clk/SM) is what bounds this kernel.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -30.f);                                   // masked columns (-inf) -> 2^-30 -> 0 in fp16
+  const float t = x + 12582912.f;                        // integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float pl = fmaf(0.0550081f, f, 0.24220917f);
+  pl = fmaf(pl, f, 0.69328282f);
+  pl = fmaf(pl, f, 1.0f);
+  return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(pl));   // (bits(t) << 23) + bits(p)
+}
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
 constexpr int kThreadsV2 = 192;
 
+// kStg: K/V pipeline depth (3 only with kPT: the P tile's 32 KB of shared memory hold the third stage)
+template <bool kPT, bool kF32, int kPoly, int kStg>
 __global__ void __launch_bounds__(kThreadsV2, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -330,17 +344,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
   const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
   uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
-  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
+  uint8_t* bar_mem = (aligned - raw >= 256) ? smem_raw : smem + kTilesBytes;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kTileBytes;
-  uint8_t* sV = sK + kKVStages * kTileBytes;
-  uint8_t* sP = sV + kKVStages * kTileBytes;
+  uint8_t* sV = sK + kStg * kTileBytes;
+  uint8_t* sP = sV + kStg * kTileBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
   uint64_t* k_full = q_full + 1;
-  uint64_t* v_full = k_full + kKVStages;
-  uint64_t* k_empty = v_full + kKVStages;
-  uint64_t* v_empty = k_empty + kKVStages;
-  uint64_t* s_full = v_empty + kKVStages;
+  uint64_t* v_full = k_full + kStg;
+  uint64_t* k_empty = v_full + kStg;
+  uint64_t* v_empty = k_empty + kStg;
+  uint64_t* s_full = v_empty + kStg;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_free + 1;
   uint64_t* o_full = p_full + 1;
@@ -357,7 +371,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < kKVStages; ++s) {
+    for (int s = 0; s < kStg; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -380,8 +394,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_expect_tx(q_full, kTileBytes);
       tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j % kKVStages;
-        const uint32_t ph = (j / kKVStages) & 1;
+        const int st = j % kStg;
+        const uint32_t ph = (j / kStg) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], kTileBytes);
         tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
@@ -395,8 +409,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);
     const uint32_t aq = smem_u32(sQ);
     auto issue_s = [&](int j) {
-      const int st = j % kKVStages;
-      mbar_wait(&k_full[st], (j / kKVStages) & 1);
+      const int st = j % kStg;
+      mbar_wait(&k_full[st], (j / kStg) & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t ak = smem_u32(sK + st * kTileBytes);
@@ -416,16 +430,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(s_free, j & 1);  // S_j now lives in the softmax warps' registers
         issue_s(j + 1);
       }
-      const int st = j % kKVStages;
+      const int st = j % kStg;
       mbar_wait(p_full, j & 1);
-      mbar_wait(&v_full[st], (j / kKVStages) & 1);
+      mbar_wait(&v_full[st], (j / kStg) & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k)
-          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
-                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        for (int k = 0; k < kBKV / 16; ++k) {
+          if (kPT)
+            umma_ts(tmem_base + kTmemO, tmem_base + 192 + k * 8, umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o,
+                    (j | k) ? 1u : 0u);
+          else
+            umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
+                    umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        }
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
       }
@@ -452,13 +471,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < kBKV; ++i)
           if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < kBKV; i += 4) {
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four chains: the 3-input max
+#pragma unroll                                                                   // has a 4-cycle dependent latency
+      for (int i = 0; i < kBKV; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
-      const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+      const float m_new = fmaxf(fmax3(mx0, mx1, mx2), mx3) * p.scale_log2;
       bool waited_o = (j == 0);
       if (j == 0) {
         m_used = m_new;
@@ -486,34 +507,58 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // probabilities for the whole row first (registers: the packed P row reuses the S row's registers) ...
       float rs = 0.f;
+      uint32_t carry = 0;
       uint32_t pk[kBKV / 2];
 #pragma unroll
       for (int c = 0; c < kBKV; c += 16) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2)
-          pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used),
-                                                 fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used)));
+        for (int i = 0; i < 16; i += 2) {
+          const float x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
+          const float x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
+          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1)
+            pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
+          else
+            pk[(c + i) >> 1] = kF32 ? cvt_f16x2(ex2(x0), ex2(x1)) : ex2_f16x2(cvt_f16x2(x0, x1));
+        }
         const uint32_t* q8 = &pk[c >> 1];
         const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
         const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
-        rs += (f0.x + f0.y) + (f1.x + f1.y);
+        if (kF32) {
+          // 16 packed pairs (32 probabilities <= 1, partial sums <= 16) summed as half2 before the fp32 accumulate
+          const uint32_t a16 = hadd2_u32(a01, a23);
+          if ((c & 16) == 0) {
+            carry = a16;
+          } else {
+            const uint32_t a32 = hadd2_u32(carry, a16);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a32));
+            rs += f.x + f.y;
+          }
+        } else {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
+          rs += (f0.x + f0.y) + (f1.x + f1.y);
+        }
       }
       // ... and only then wait for the previous P V to release the P tile: the exponentials above ran under it
       if (!waited_o) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
+      if (kPT) {
+        tmem_st32(tmem_addr(tmem_base, lane_base, 192), &pk[0]);
+        tmem_st32(tmem_addr(tmem_base, lane_base, 224), &pk[32]);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int c = 0; c < kBKV; c += 8) {
-        const uint32_t addr = p_row + (c >> 6) * (kBQ * 128) + (((((c & 63) >> 3)) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]), "r"(pk[(c >> 1) + 1]),
-                     "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
-                     : "memory");
+        for (int c = 0; c < kBKV; c += 8) {
+          const uint32_t addr = p_row + (c >> 6) * (kBQ * 128) + (((((c & 63) >> 3)) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]),
+                       "r"(pk[(c >> 1) + 1]), "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
       }
       l_run += rs;
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
@@ -556,20 +601,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // partial row maximum (every tile) and partial row sum (once, at the end) through spare TMEM columns -- there is no
 // shared memory left (2 CTAs x 113 KB) -- and meet on a 64-thread named barrier per warp pair.
 constexpr int kThreadsV3 = 320;           // warps 0..7 softmax, warp 8 TMA, warp 9 MMA
-constexpr int kPolyEvery = 4;             // every kPolyEvery-th pair of exponentials runs on the FMA pipe (0 = none)
 
-// 2^x on the FMA pipe: Cody-Waite split with the 1.5*2^23 rounding constant, cubic for 2^f on [-0.5, 0.5]
-// (max relative error 1.0e-4 < fp16 rounding), exponent re-inserted with one integer multiply-add.
-// 1 ALU + 6 FMA-pipe instructions instead of one MUFU.EX2: the exp unit (16 lanes/clk/SM) is what bounds this kernel.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -30.f);                                   // masked columns (-inf) -> 2^-30 -> 0 in fp16
-  const float t = x + 12582912.f;                        // integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);
-  float pl = fmaf(0.0550081f, f, 0.24220917f);
-  pl = fmaf(pl, f, 0.69328282f);
-  pl = fmaf(pl, f, 1.0f);
-  return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(pl));   // (bits(t) << 23) + bits(p)
-}
 constexpr uint32_t kTmemX = 192;          // exchange columns: [kTmemX + 2*parity + half]
 
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
@@ -595,7 +627,26 @@ __device__ __forceinline__ float pair_exchange(uint32_t tmem_base, uint32_t lane
   tmem_ld_wait();
   return __uint_as_float(other);
 }
+// the same through shared memory (v4: the P tile lives in TMEM, so its 32 KB of shared memory are free)
+__device__ __forceinline__ float pair_exchange_smem(uint32_t xch, int quad, int half, int slot, int row, float mine) {
+  float other;
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(xch + (uint32_t)(((slot * 2 + half) * kBQ + row) * 4)), "f"(mine)
+               : "memory");
+  pair_barrier(quad);
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(other) : "r"(xch + (uint32_t)(((slot * 2 + (half ^ 1)) * kBQ + row) * 4))
+               : "memory");
+  return other;
+}
 
+// kPT (v4): the probabilities go to TMEM columns [kTmemP, kTmemP + 64) as packed halfs and P V is issued with the
+// A operand read from TMEM (tcgen05.mma [d], [a], b-desc).  That removes 64 KB of shared-memory traffic per tile
+// (32 KB of st.shared + 32 KB of operand fetch) from a kernel whose K/V/Q operand fetch and TMA fills already use
+// 80 KB per tile of the SM's 128 B/clk.
+constexpr uint32_t kTmemP = 192;
+// kF32: exponentials as scalar ex2.approx.f32 packed afterwards (2 FFMA + 2 MUFU + 1 F2FP per pair) instead of
+// ex2.approx.f16x2, which ptxas splits into 2 MUFU.EX2.F16 + a PRMT on top of the F2FP that feeds it.
+// kPoly: every kPoly-th pair of exponentials runs on the FMA pipe (0 = none).
+template <bool kPT, bool kF32, int kPoly>
 __global__ void __launch_bounds__(kThreadsV3, 2)
 attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -696,15 +747,21 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (lane == 0) {
         const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k)
-          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
-                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        for (int k = 0; k < kBKV / 16; ++k) {
+          if (kPT)
+            umma_ts(tmem_base + kTmemO, tmem_base + kTmemP + k * 8, umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o,
+                    (j | k) ? 1u : 0u);
+          else
+            umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
+                    umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
+        }
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
       }
       __syncwarp();
     }
   } else {
+    const uint32_t xch = smem_u32(sP);
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32);
@@ -735,7 +792,9 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
       }
       const float mine = fmaxf(mx0, mx1);
-      const float m_new = fmaxf(mine, pair_exchange(tmem_base, lane_base, quad, half, j & 1, mine)) * p.scale_log2;
+      const float theirs = kPT ? pair_exchange_smem(xch, quad, half, j & 1, row, mine)
+                               : pair_exchange(tmem_base, lane_base, quad, half, j & 1, mine);
+      const float m_new = fmaxf(mine, theirs) * p.scale_log2;
       bool waited_o = (j == 0);
       if (j == 0) {
         m_used = m_new;
@@ -761,6 +820,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       }
       float rs = 0.f;
+      uint32_t carry = 0;
       uint32_t pk[kHalf / 2];
 #pragma unroll
       for (int c = 0; c < kHalf; c += 16) {
@@ -768,37 +828,57 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int i = 0; i < 16; i += 2) {
           const float x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
           const float x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
-          if (kPolyEvery > 0 && ((i >> 1) % kPolyEvery) == kPolyEvery - 1)
+          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1)
             pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
+          else if (kF32)
+            pk[(c + i) >> 1] = cvt_f16x2(ex2(x0), ex2(x1));
           else
             pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(x0, x1));
         }
         const uint32_t* q8 = &pk[c >> 1];
         const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
         const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
-        rs += (f0.x + f0.y) + (f1.x + f1.y);
+        if (kF32) {
+          // 16 packed pairs (32 probabilities <= 1, partial sums <= 16) summed as half2 before the fp32 accumulate
+          const uint32_t a16 = hadd2_u32(a01, a23);
+          if ((c & 16) == 0) {
+            carry = a16;
+          } else {
+            const uint32_t a32 = hadd2_u32(carry, a16);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a32));
+            rs += f.x + f.y;
+          }
+        } else {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
+          rs += (f0.x + f0.y) + (f1.x + f1.y);
+        }
       }
       l_part += rs;
       if (!waited_o) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
+      if (kPT) {
+        tmem_st32(tmem_addr(tmem_base, lane_base, kTmemP + half * (kHalf / 2)), pk);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int c = 0; c < kHalf; c += 8) {
-        const uint32_t addr = p_row + ((((c >> 3)) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]), "r"(pk[(c >> 1) + 1]),
-                     "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
-                     : "memory");
+        for (int c = 0; c < kHalf; c += 8) {
+          const uint32_t addr = p_row + ((((c >> 3)) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]),
+                       "r"(pk[(c >> 1) + 1]), "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
-    const float l_tot = l_part + pair_exchange(tmem_base, lane_base, quad, half, n_kv & 1, l_part);
+    const float l_tot = l_part + (kPT ? pair_exchange_smem(xch, quad, half, n_kv & 1, row, l_part)
+                                      : pair_exchange(tmem_base, lane_base, quad, half, n_kv & 1, l_part));
     const float inv_l = 1.f / l_tot;
     const int qrow = q0 + row;
     __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl + half * (kD / 2);
@@ -825,6 +905,20 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
+
+using AttnKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+// [0] = v3 (P through shared memory); [1..] = v4 flavours (P in TMEM): exp as f16x2 / f32, share of polynomial exps
+const AttnKernel kV3Variants[] = {
+    attention_kernel_v3<false, false, 4>, attention_kernel_v3<true, false, 4>, attention_kernel_v3<true, true, 0>,
+    attention_kernel_v3<true, true, 8>,   attention_kernel_v3<true, true, 6>,  attention_kernel_v3<true, true, 4>,
+    attention_kernel_v3<true, false, 0>,  attention_kernel_v3<true, true, 12>, attention_kernel_v3<true, true, 16>,
+};
+
+// one thread per row: [0] = v2 as measured in r1c; [1] P in TMEM; [2] P in TMEM + f32 exponentials
+const AttnKernel kV2Variants[] = {attention_kernel<false, false, 0, 2>, attention_kernel<true, false, 0, 2>,
+                                  attention_kernel<true, true, 0, 2>,   attention_kernel<true, true, 8, 2>,
+                                  attention_kernel<true, true, 6, 2>,   attention_kernel<true, true, 4, 2>,
+                                  attention_kernel<true, true, 8, 3>,   attention_kernel<true, true, 12, 2>};
 
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
                  int L) {
@@ -855,17 +949,25 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
   static bool use_v1 = false;
-  static int version = 3;   // R3G_ATTN=1|2|3 selects the kernel generation (parity tests run all of them)
+  static int variant = 4, variant2 = 3;
+  static int version = 2;   // R3G_ATTN=1|2|3|4 selects the kernel generation (parity tests run all of them)
   if (!attr_set) {
     const char* e = getenv("R3G_ATTN_V1");
     use_v1 = e && e[0] == '1';
     const char* ev = getenv("R3G_ATTN");
-    if (ev && ev[0] >= '1' && ev[0] <= '3') version = ev[0] - '0';
+    if (ev && ev[0] >= '1' && ev[0] <= '4') version = ev[0] - '0';
     if (use_v1) version = 1;
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v3, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (AttnKernel fn : kV3Variants) {
+      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    const char* evar = getenv("R3G_ATTN_VARIANT");   // experiments: index into kV3Variants (version 4 only)
+    if (evar && evar[0] >= '0' && evar[0] < '0' + (int)(sizeof(kV3Variants) / sizeof(kV3Variants[0]))) variant = evar[0] - '0';
+    if (evar && evar[0] >= '0' && evar[0] < '0' + (int)(sizeof(kV2Variants) / sizeof(kV2Variants[0]))) variant2 = evar[0] - '0';
+    for (AttnKernel fn : kV2Variants) {
+      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
@@ -874,9 +976,9 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   if (version == 1)
     attention_kernel_v1<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   else if (version == 2)
-    attention_kernel<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    kV2Variants[variant2]<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   else
-    attention_kernel_v3<<<grid, kThreadsV3, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    kV3Variants[version == 3 ? 0 : variant]<<<grid, kThreadsV3, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
