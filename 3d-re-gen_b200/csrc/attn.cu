@@ -331,12 +331,52 @@ __device__ __forceinline__ float exp2_poly(float x) {
   pl = fmaf(pl, f, 1.0f);
   return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(pl));   // (bits(t) << 23) + bits(p)
 }
+// Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issued instruction, operands in
+// aligned 64-bit register pairs -- the S row arrives from tcgen05.ld already laid out that way).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// exp2_poly on a pair: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 IMAD for two results
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float& e1) {
+  const uint64_t x = f2_pack(fmaxf(x0, -30.f), fmaxf(x1, -30.f));
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f), nmagic = f2_pack(-12582912.f, -12582912.f);
+  const uint64_t t = f2_add(x, magic);
+  const uint64_t ti = f2_add(t, nmagic);
+  float i0, i1;
+  f2_unpack(ti, i0, i1);
+  const uint64_t f = f2_add(x, f2_pack(-i0, -i1));
+  uint64_t pl = f2_fma(f2_pack(0.0550081f, 0.0550081f), f, f2_pack(0.24220917f, 0.24220917f));
+  pl = f2_fma(pl, f, f2_pack(0.69328282f, 0.69328282f));
+  pl = f2_fma(pl, f, f2_pack(1.0f, 1.0f));
+  float t0, t1, p0, p1;
+  f2_unpack(t, t0, t1);
+  f2_unpack(pl, p0, p1);
+  e0 = __int_as_float(__float_as_int(t0) * 8388608 + __float_as_int(p0));
+  e1 = __int_as_float(__float_as_int(t1) * 8388608 + __float_as_int(p1));
+}
+
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
 constexpr int kThreadsV2 = 192;
 
 // kStg: K/V pipeline depth (3 only with kPT: the P tile's 32 KB of shared memory hold the third stage)
-template <bool kPT, bool kF32, int kPoly, int kStg>
+// kF2: scale-and-subtract and the polynomial exponentials on the packed fp32 pipe (FFMA2 / FADD2)
+template <bool kPT, bool kF32, int kPoly, int kStg, bool kF2 = false>
 __global__ void __launch_bounds__(kThreadsV2, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -508,17 +548,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // probabilities for the whole row first (registers: the packed P row reuses the S row's registers) ...
       float rs = 0.f;
       uint32_t carry = 0;
+      const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(-m_used, -m_used);
       uint32_t pk[kBKV / 2];
 #pragma unroll
       for (int c = 0; c < kBKV; c += 16) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          const float x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
-          const float x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
-          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1)
-            pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
-          else
+          float x0, x1;
+          if (kF2) {
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 1])), scale2, nm2), x0, x1);
+          } else {
+            x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
+            x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
+          }
+          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1) {
+            if (kF2) {
+              float e0, e1;
+              exp2_poly2(x0, x1, e0, e1);
+              pk[(c + i) >> 1] = cvt_f16x2(e0, e1);
+            } else {
+              pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
+            }
+          } else {
             pk[(c + i) >> 1] = kF32 ? cvt_f16x2(ex2(x0), ex2(x1)) : ex2_f16x2(cvt_f16x2(x0, x1));
+          }
         }
         const uint32_t* q8 = &pk[c >> 1];
         const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
@@ -918,7 +971,8 @@ const AttnKernel kV3Variants[] = {
 const AttnKernel kV2Variants[] = {attention_kernel<false, false, 0, 2>, attention_kernel<true, false, 0, 2>,
                                   attention_kernel<true, true, 0, 2>,   attention_kernel<true, true, 8, 2>,
                                   attention_kernel<true, true, 6, 2>,   attention_kernel<true, true, 4, 2>,
-                                  attention_kernel<true, true, 8, 3>,   attention_kernel<true, true, 12, 2>};
+                                  attention_kernel<true, true, 8, 2, true>, attention_kernel<true, true, 4, 2, true>,
+                                  attention_kernel<true, true, 6, 2, true>, attention_kernel<true, true, 3, 2, true>};
 
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
                  int L) {
@@ -949,7 +1003,7 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
   static bool use_v1 = false;
-  static int variant = 4, variant2 = 3;
+  static int variant = 4, variant2 = 7;
   static int version = 2;   // R3G_ATTN=1|2|3|4 selects the kernel generation (parity tests run all of them)
   if (!attr_set) {
     const char* e = getenv("R3G_ATTN_V1");

@@ -38,7 +38,99 @@ __device__ __forceinline__ Half8 pack8(const float* f) {
 // One warp per row; the row (<= 2048 halfs) lives in registers between the statistics and the write.
 constexpr int kLnMaxChunks = 8;  // 8 chunks * 32 lanes * 8 halfs = 2048
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t ldx,
+// Rows are walked by persistent warps; the NEXT row's 16-byte loads are issued (into packed registers) before the
+// current row is reduced, so every warp always has a full row in flight.  NCH = chunks of 8 halfs per lane
+// (4: width <= 1024, 8: width <= 2048).  The arithmetic runs on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2,
+// two IEEE fp32 results per instruction) and the affine weights sit in shared memory as fp32: at 6.5 TB/s an fp16
+// LayerNorm has a budget of ~10 issue slots per element, the scalar version spent 11 and ran at 2.6 TB/s
+// (profiles/README.md r1f).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_h2(uint64_t v) {   // round a pair to packed fp16 (lo in the low half)
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint64_t h2_to_f2(uint32_t h) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  return f2_pack(f.x, f.y);
+}
+
+template <int NCH>
+__device__ __forceinline__ void load_row(Half8 (&d)[NCH], const Half8* xr, int lane, int nchunks) {
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nchunks) d[j] = xr[c];
+  }
+}
+
+// widen a packed row to fp32 pairs; returns the lane's partial sum.  Chunks beyond nchunks are never touched.
+template <int NCH>
+__device__ __forceinline__ float widen_row(const Half8 (&raw)[NCH], uint64_t (&d)[NCH][4], int lane, int nchunks) {
+  uint64_t s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    if (lane + 32 * j < nchunks) {
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(&raw[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        d[j][k] = h2_to_f2(hw[k]);
+        s2 = f2_add(s2, d[j][k]);
+      }
+    }
+  }
+  float s0, s1;
+  f2_unpack(s2, s0, s1);
+  return s0 + s1;
+}
+// d <- d - mean; returns rstd
+template <int NCH>
+__device__ __forceinline__ float center_row(uint64_t (&d)[NCH][4], float lane_sum, int lane, int nchunks, int width,
+                                            float eps) {
+  const float mean = warp_sum(lane_sum) / (float)width;
+  const uint64_t nmean = f2_pack(-mean, -mean);
+  uint64_t q2 = f2_pack(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    if (lane + 32 * j < nchunks) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        d[j][k] = f2_add(d[j][k], nmean);
+        q2 = f2_fma(d[j][k], d[j][k], q2);
+      }
+    }
+  }
+  float q0, q1;
+  f2_unpack(q2, q0, q1);
+  return rsqrtf(warp_sum(q0 + q1) / (float)width + eps);
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256, NCH == 4 ? 3 : 2) layernorm_kernel(const __half* __restrict__ x, int64_t ldx,
                                                         __half* __restrict__ y, int64_t ldy, int rows, int width,
                                                         float eps, const __half* __restrict__ w,
                                                         const __half* __restrict__ b,
@@ -46,68 +138,69 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const __half* __restrict__ shift, int64_t mod_ld,
                                                         int rows_per_batch, int seg_len, int64_t x_seg_stride,
                                                         int64_t y_seg_stride) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float ln_wb[];   // [width] weight (1 if absent), [width] bias (0 if absent)
+  if (w || b) {
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+      ln_wb[i] = w ? h2f(w[i]) : 1.f;
+      ln_wb[width + i] = b ? h2f(b[i]) : 0.f;
+    }
+    __syncthreads();
+  }
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nchunks = width >> 3;
-  float v[kLnMaxChunks][8];
-  float s = 0.f;
-  int64_t xrow = row, yrow = row;
-  if (seg_len > 0) {
-    const int sg = row / seg_len, l = row - sg * seg_len;
-    xrow = sg * x_seg_stride + l;
-    yrow = sg * y_seg_stride + l;
-  }
-  const Half8* xr = reinterpret_cast<const Half8*>(x + xrow * ldx);
+  auto x_row = [&](int r) {
+    int64_t xr = r;
+    if (seg_len > 0) xr = (int64_t)(r / seg_len) * x_seg_stride + (r % seg_len);
+    return reinterpret_cast<const Half8*>(x + xr * ldx);
+  };
+  Half8 nxt[NCH];
+  load_row<NCH>(nxt, x_row(row), lane, nchunks);
+  for (; row < rows; row += nwarps) {
+    uint64_t d[NCH][4];
+    const float lane_sum = widen_row<NCH>(nxt, d, lane, nchunks);
+    if (row + nwarps < rows) load_row<NCH>(nxt, x_row(row + nwarps), lane, nchunks);   // in flight under the math
+    const float rstd = center_row<NCH>(d, lane_sum, lane, nchunks, width, eps);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
+    int64_t yrow = row;
+    if (seg_len > 0) yrow = (int64_t)(row / seg_len) * y_seg_stride + (row % seg_len);
+    const int bi = rows_per_batch > 0 ? row / rows_per_batch : 0;
+    Half8* yr = reinterpret_cast<Half8*>(y + yrow * ldy);
 #pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-      Half8 p = xr[c];
-      unpack8(p, v[j]);
+    for (int j = 0; j < NCH; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) {
+        uint32_t o[4];
+        if (w || b) {
+          const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(ln_wb + 8 * c);
+          const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(ln_wb + width + 8 * c);
+          const ulonglong2 w01 = wp[0], w23 = wp[1], b01 = bp[0], b23 = bp[1];
+          o[0] = f2_to_h2(f2_fma(f2_mul(d[j][0], rstd2), w01.x, b01.x));
+          o[1] = f2_to_h2(f2_fma(f2_mul(d[j][1], rstd2), w01.y, b01.y));
+          o[2] = f2_to_h2(f2_fma(f2_mul(d[j][2], rstd2), w23.x, b23.x));
+          o[3] = f2_to_h2(f2_fma(f2_mul(d[j][3], rstd2), w23.y, b23.y));
+        } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[j][i];
-    }
-  }
-  const float mean = warp_sum(s) / (float)width;
-  float q = 0.f;
+          for (int k = 0; k < 4; ++k) o[k] = f2_to_h2(f2_mul(d[j][k], rstd2));
+        }
+        if (scale) {
+          // reference: (1 + scale) * LN(x) + shift, every op rounded to fp16 (hunyuan3ddit.py:193).  The operands
+          // are halfs, so each fp32-then-round step equals the IEEE half operation: done as three half2 instructions.
+          const Half8 sc = reinterpret_cast<const Half8*>(scale + (int64_t)bi * mod_ld)[c];
+          const Half8 sh = reinterpret_cast<const Half8*>(shift + (int64_t)bi * mod_ld)[c];
+          const __half2* sc2 = reinterpret_cast<const __half2*>(&sc);
+          const __half2* sh2 = reinterpret_cast<const __half2*>(&sh);
+          const __half2 one = __floats2half2_rn(1.f, 1.f);
 #pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float d = v[j][i] - mean;
-        q += d * d;
+          for (int k = 0; k < 4; ++k) {
+            const __half2 t = __hadd2(__hmul2(__hadd2(one, sc2[k]), *reinterpret_cast<const __half2*>(&o[k])), sh2[k]);
+            o[k] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+        }
+        yr[c] = *reinterpret_cast<const Half8*>(o);
       }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
-  const int bi = rows_per_batch > 0 ? row / rows_per_batch : 0;
-  Half8* yr = reinterpret_cast<Half8*>(y + yrow * ldy);
-#pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-      float o[8], wf[8], bf[8];
-      if (w) { unpack8(reinterpret_cast<const Half8*>(w)[c], wf); }
-      if (b) { unpack8(reinterpret_cast<const Half8*>(b)[c], bf); }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = (v[j][i] - mean) * rstd;
-        if (w) t = t * wf[i];
-        if (b) t = t + bf[i];
-        o[i] = t;
-      }
-      if (scale) {
-        // reference: (1 + scale) * LN(x) + shift, every op rounded to fp16 (hunyuan3ddit.py:193)
-        float sc[8], sh[8];
-        unpack8(reinterpret_cast<const Half8*>(scale + (int64_t)bi * mod_ld)[c], sc);
-        unpack8(reinterpret_cast<const Half8*>(shift + (int64_t)bi * mod_ld)[c], sh);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rnd_h(rnd_h(1.f + sc[i]) * rnd_h(o[i])) + sh[i];
-      }
-      yr[c] = pack8(o);
     }
   }
 }
@@ -326,45 +419,72 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------- GEMV (M <= 8)
 constexpr int kGemvMaxB = 8;
+constexpr int kGemvRows = 4;   // output rows per warp, their weight loads issued together (bytes in flight)
+// The activated input vectors are staged once per block in shared memory (the first version re-evaluated
+// silu() -- an expf and a divide -- for every output row and ran at 1.0 TB/s, MUFU-bound; profiles/README.md r1f).
+template <int BT>
 __global__ void __launch_bounds__(256) gemv_kernel(const __half* __restrict__ w, const __half* __restrict__ bias,
                                                    const __half* __restrict__ vec, int64_t vec_ld,
                                                    __half* __restrict__ out, int64_t out_ld, int B, int N, int K,
                                                    int silu_in, int silu_out) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
+  extern __shared__ float gemv_x[];   // [BT][K]
+  for (int i = threadIdx.x; i < BT * K; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    float xv = 0.f;
+    if (b < B) {
+      xv = h2f(vec[(int64_t)b * vec_ld + k]);
+      if (silu_in) xv = rnd_h(xv / (1.f + expf(-xv)));
+    }
+    gemv_x[i] = xv;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  float acc[kGemvMaxB];
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kGemvRows;
+  if (n0 >= N) return;
+  float acc[kGemvRows][BT];
 #pragma unroll
-  for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
-  const Half8* wr = reinterpret_cast<const Half8*>(w + (int64_t)n * K);
-  for (int c = lane; c < (K >> 3); c += 32) {
-    float wf[8];
-    unpack8(wr[c], wf);
+  for (int r = 0; r < kGemvRows; ++r)
 #pragma unroll
-    for (int b = 0; b < kGemvMaxB; ++b) {
-      if (b < B) {
-        float xf[8];
-        unpack8(reinterpret_cast<const Half8*>(vec + (int64_t)b * vec_ld)[c], xf);
+    for (int b = 0; b < BT; ++b) acc[r][b] = 0.f;
+  const int nch = K >> 3;
+  for (int c = lane; c < nch; c += 32) {
+    Half8 wv[kGemvRows];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float xv = xf[i];
-          if (silu_in) xv = rnd_h(xv / (1.f + expf(-xv)));
-          acc[b] += wf[i] * xv;
-        }
-      }
+    for (int r = 0; r < kGemvRows; ++r) {
+      const int n = min(n0 + r, N - 1);
+      wv[r] = reinterpret_cast<const Half8*>(w + (int64_t)n * K)[c];
+    }
+    float xf[BT][8];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const float4 lo = reinterpret_cast<const float4*>(gemv_x + b * K)[2 * c];
+      const float4 hi = reinterpret_cast<const float4*>(gemv_x + b * K)[2 * c + 1];
+      xf[b][0] = lo.x; xf[b][1] = lo.y; xf[b][2] = lo.z; xf[b][3] = lo.w;
+      xf[b][4] = hi.x; xf[b][5] = hi.y; xf[b][6] = hi.z; xf[b][7] = hi.w;
+    }
+#pragma unroll
+    for (int r = 0; r < kGemvRows; ++r) {
+      float wf[8];
+      unpack8(wv[r], wf);
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][b] += wf[i] * xf[b][i];
     }
   }
 #pragma unroll
-  for (int b = 0; b < kGemvMaxB; ++b) {
-    if (b < B) {
-      float r = warp_sum(acc[b]);
-      if (lane == 0) {
-        if (bias) r += h2f(bias[n]);
+  for (int r = 0; r < kGemvRows; ++r) {
+    const int n = n0 + r;
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      float v = warp_sum(acc[r][b]);
+      if (lane == 0 && n < N && b < B) {
+        if (bias) v += h2f(bias[n]);
         if (silu_out) {
-          r = rnd_h(r);
-          r = r / (1.f + expf(-r));
+          v = rnd_h(v);
+          v = v / (1.f + expf(-v));
         }
-        out[(int64_t)b * out_ld + n] = __float2half_rn(r);
+        out[(int64_t)b * out_ld + n] = __float2half_rn(v);
       }
     }
   }
@@ -444,13 +564,34 @@ __global__ void __launch_bounds__(256) points_fourier_kernel(const __half* __res
 }
 
 __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi) {
+  if (F == 8 && out_ld == 64 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    // the geo-decoder's shape: the 51 features + 13 zeros of a row are built in registers and leave as eight
+    // 16-byte stores (a thread owns 128 contiguous bytes) instead of 64 strided 2-byte ones
+    __half r[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) r[c] = __float2half_rn(0.f);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      r[d] = __float2half_rn(xh[d]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float f = (float)(1 << k);
+        if (include_pi) f = rnd_h(f * 3.14159265358979323846f);
+        const float e = rnd_h(xh[d] * f);
+        r[3 + d * 8 + k] = __float2half_rn(sinf(e));
+        r[3 + 24 + d * 8 + k] = __float2half_rn(cosf(e));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(o)[c] = reinterpret_cast<const uint4*>(r)[c];
+    return;
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) o[d] = __float2half_rn(xh[d]);
-  struct { int num_freqs; int include_pi; } gp = {F, include_pi};
   for (int d = 0; d < 3; ++d)
     for (int k = 0; k < F; ++k) {
       float f = (float)(1 << k);
-      if (gp.include_pi) f = rnd_h(f * 3.14159265358979323846f);
+      if (include_pi) f = rnd_h(f * 3.14159265358979323846f);
       const float e = rnd_h(xh[d] * f);  // fp16 product (frequencies buffer is cast to fp16 with the module)
       o[3 + d * F + k] = __float2half_rn(sinf(e));
       o[3 + 3 * F + d * F + k] = __float2half_rn(cosf(e));
@@ -459,56 +600,54 @@ __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const flo
 }
 
 // ------------------------------------------------------------------------------------------- ln_post + output_proj
-__global__ void __launch_bounds__(256) lnpost_dot_kernel(const __half* __restrict__ x, int64_t ldx, int rows,
+template <int NCH>
+__global__ void __launch_bounds__(256, NCH == 4 ? 3 : 2) lnpost_dot_kernel(const __half* __restrict__ x, int64_t ldx, int rows,
                                                          int width, float eps, const __half* __restrict__ ln_w,
                                                          const __half* __restrict__ ln_b,
                                                          const __half* __restrict__ w_out,
                                                          const __half* __restrict__ b_out, float* __restrict__ out) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float lp_c[];   // [width] ln weight, [width] ln bias, [width] output_proj weight
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    lp_c[i] = h2f(ln_w[i]);
+    lp_c[width + i] = h2f(ln_b[i]);
+    lp_c[2 * width + i] = h2f(w_out[i]);
+  }
+  __syncthreads();
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nchunks = width >> 3;
-  float v[kLnMaxChunks][8];
-  float s = 0.f;
-  const Half8* xr = reinterpret_cast<const Half8*>(x + (int64_t)row * ldx);
+  Half8 nxt[NCH];
+  load_row<NCH>(nxt, reinterpret_cast<const Half8*>(x + (int64_t)row * ldx), lane, nchunks);
+  for (; row < rows; row += nwarps) {
+    uint64_t d[NCH][4];
+    const float lane_sum = widen_row<NCH>(nxt, d, lane, nchunks);
+    if (row + nwarps < rows)
+      load_row<NCH>(nxt, reinterpret_cast<const Half8*>(x + (int64_t)(row + nwarps) * ldx), lane, nchunks);
+    const float rstd = center_row<NCH>(d, lane_sum, lane, nchunks, width, eps);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
+    uint64_t acc2 = f2_pack(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-      unpack8(xr[c], v[j]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[j][i];
-    }
-  }
-  const float mean = warp_sum(s) / (float)width;
-  float q = 0.f;
-#pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float d = v[j][i] - mean;
-        q += d * d;
+    for (int j = 0; j < NCH; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) {
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(lp_c + 8 * c);
+        const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(lp_c + width + 8 * c);
+        const ulonglong2* op = reinterpret_cast<const ulonglong2*>(lp_c + 2 * width + 8 * c);
+        const ulonglong2 w01 = wp[0], w23 = wp[1], b01 = bp[0], b23 = bp[1], o01 = op[0], o23 = op[1];
+        // ln_post output is an fp16 tensor (rounded), the 1024 -> 1 projection accumulates in fp32
+        acc2 = f2_fma(h2_to_f2(f2_to_h2(f2_fma(f2_mul(d[j][0], rstd2), w01.x, b01.x))), o01.x, acc2);
+        acc2 = f2_fma(h2_to_f2(f2_to_h2(f2_fma(f2_mul(d[j][1], rstd2), w01.y, b01.y))), o01.y, acc2);
+        acc2 = f2_fma(h2_to_f2(f2_to_h2(f2_fma(f2_mul(d[j][2], rstd2), w23.x, b23.x))), o23.x, acc2);
+        acc2 = f2_fma(h2_to_f2(f2_to_h2(f2_fma(f2_mul(d[j][3], rstd2), w23.y, b23.y))), o23.y, acc2);
       }
     }
+    float a0, a1;
+    f2_unpack(acc2, a0, a1);
+    const float acc = warp_sum(a0 + a1);
+    if (lane == 0) out[row] = rnd_h(acc + (b_out ? h2f(b_out[0]) : 0.f));
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)width + eps);
-  float acc = 0.f;
-#pragma unroll
-  for (int j = 0; j < kLnMaxChunks; ++j) {
-    const int c = lane + 32 * j;
-    if (c < nchunks) {
-      float wf[8], bf[8], of[8];
-      unpack8(reinterpret_cast<const Half8*>(ln_w)[c], wf);
-      unpack8(reinterpret_cast<const Half8*>(ln_b)[c], bf);
-      unpack8(reinterpret_cast<const Half8*>(w_out)[c], of);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc += rnd_h((v[j][i] - mean) * rstd * wf[i] + bf[i]) * of[i];
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) out[row] = rnd_h(acc + (b_out ? h2f(b_out[0]) : 0.f));
 }
 
 // ------------------------------------------------------------------------------------------- back-projection
@@ -596,9 +735,17 @@ extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, 
                     kLnMaxChunks * 256);
   if ((scale == nullptr) != (shift == nullptr)) return r3g_fail(ctx, R3G_E_INVALID, "layernorm: scale/shift pair");
   if (rows <= 0) return R3G_OK;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, rows, width, eps, (const __half*)w, (const __half*)b,
-      (const __half*)scale, (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride, y_seg_stride);
+  // persistent beyond one resident wave (3 blocks per SM at width <= 1024, 2 above)
+  const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
+  const size_t smem = (w || b) ? (size_t)2 * width * sizeof(float) : 0;
+  auto go = [&](auto kern) {
+    kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, width, eps,
+                                                 (const __half*)w, (const __half*)b, (const __half*)scale,
+                                                 (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride,
+                                                 y_seg_stride);
+  };
+  if (width <= 1024) go(layernorm_kernel<4>);
+  else go(layernorm_kernel<8>);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -668,9 +815,18 @@ extern "C" int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const voi
   R3G_NEED_GPU(ctx, "gemv");
   if (B < 1 || B > kGemvMaxB || K % 8 || vec_ld % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "gemv: B in [1,%d], K %% 8 == 0 required", kGemvMaxB);
-  gemv_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)w, (const __half*)bias,
-                                                               (const __half*)vec, vec_ld, (__half*)out, out_ld, B, N,
-                                                               K, silu_in, silu_out);
+  const int bt = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8;
+  const size_t smem = (size_t)bt * K * sizeof(float);
+  if (smem > 48 * 1024) return r3g_fail(ctx, R3G_E_INVALID, "gemv: B_pad * K * 4 bytes must fit 48 KB of shared memory");
+  const unsigned grid = (unsigned)((N + 8 * kGemvRows - 1) / (8 * kGemvRows));
+  auto args = [&](auto kern) {
+    kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)w, (const __half*)bias, (const __half*)vec, vec_ld,
+                                                    (__half*)out, out_ld, B, N, K, silu_in, silu_out);
+  };
+  if (bt == 1) args(gemv_kernel<1>);
+  else if (bt == 2) args(gemv_kernel<2>);
+  else if (bt == 4) args(gemv_kernel<4>);
+  else args(gemv_kernel<8>);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -735,10 +891,13 @@ extern "C" int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows
   R3G_NEED_GPU(ctx, "lnpost_dot");
   if (width % 8 || width > kLnMaxChunks * 256 || ldx % 8) return r3g_fail(ctx, R3G_E_INVALID, "lnpost_dot: width");
   if (rows <= 0) return R3G_OK;
-  lnpost_dot_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, rows, width, eps,
-                                                                        (const __half*)ln_w, (const __half*)ln_b,
-                                                                        (const __half*)w_out, (const __half*)b_out,
-                                                                        out);
+  const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
+  auto go = [&](auto kern) {
+    kern<<<grid, 256, (size_t)3 * width * sizeof(float), (cudaStream_t)stream>>>((const __half*)x, ldx, rows, width, eps, (const __half*)ln_w,
+                                                 (const __half*)ln_b, (const __half*)w_out, (const __half*)b_out, out);
+  };
+  if (width <= 1024) go(lnpost_dot_kernel<4>);
+  else go(lnpost_dot_kernel<8>);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -255,8 +255,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), h2d, d2h, (ctx.launches + pipe.replayed_launches - launches0), meshes
 
-    for i in range(W):  # warm-up (also captures the DiT CUDA graph)
-        run_object(dev_in[i], 1234567 + i)
+    # warm-up (also captures the DiT CUDA graph).  The warm-up meshes are held like the timed loop holds its own
+    # (K device-resident meshes until the gather) and released together, so that torch's caching allocator enters
+    # the timed region with K sets of ~200 MB mesh blocks: a fresh cudaMalloc of that size costs 50-100 ms here
+    # and would otherwise be charged to 2 of every 3 timed objects (profiles/README.md r1f).
+    warm = [run_object(dev_in[i], 1234567 + i) for i in range(W)]
+    del warm
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

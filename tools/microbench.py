@@ -77,6 +77,42 @@ def main():
         out.append(dict(op="marching_cubes", n=n, ms=ms, verts=len(v), faces=len(f),
                         grid_gbs=n ** 3 * 4 * 3 / ms / 1e6))
         print(out[-1], flush=True)
+    if not only or "rowops" in only:
+        def rec(name, fn, nbytes, **kw):
+            for fl in (True, False):
+                ms = timeit(fn, iters=20, flush=fl)
+                out.append(dict(op=name, l2="flushed" if fl else "warm", us=ms * 1e3, gbs=nbytes / ms / 1e6, **kw))
+                print(out[-1], flush=True)
+        W = 1024
+        for rows, B in ((6144, 2), (8884, 2)):   # DiT: modulated LayerNorm of the img stream / the joint stream
+            x = torch.randn(rows, W, device="cuda").half()
+            sc, sh = torch.randn(B, W, device="cuda").half(), torch.randn(B, W, device="cuda").half()
+            y = torch.empty_like(x)
+            rec("layernorm_mod", lambda: ops.layernorm(x, eps=1e-6, scale=sc, shift=sh, rows_per_batch=rows // B, out=y),
+                rows * W * 4, rows=rows)
+        for rows in (65536,):                     # decode: affine LayerNorm, q LayerNorm per head, ln_post + dot
+            x = torch.randn(rows, W, device="cuda").half()
+            g, b_ = torch.randn(W, device="cuda").half(), torch.randn(W, device="cuda").half()
+            y = torch.empty_like(x)
+            rec("layernorm_affine", lambda: ops.layernorm(x, g, b_, eps=1e-6, out=y), rows * W * 4, rows=rows)
+            g64, b64 = torch.randn(64, device="cuda").half(), torch.randn(64, device="cuda").half()
+            rec("qk_norm_ln_q", lambda: ops.qk_norm_(x, 16, 0, 0, 64, 1, 1e-6, g64, b64), rows * W * 4, rows=rows)
+            wo, bo = torch.randn(W, device="cuda").half(), torch.randn(1, device="cuda").half()
+            o32 = torch.empty(rows, device="cuda", dtype=torch.float32)
+            rec("lnpost_dot", lambda: ops.lnpost_dot(x, g, b_, wo, bo, o32, eps=1e-5), rows * W * 2, rows=rows)
+            emb = torch.empty(rows, 64, device="cuda", dtype=torch.float16)
+            rec("grid_fourier", lambda: ops.grid_fourier(emb, 0, rows, 256, [-1.01] * 3 + [1.01] * 3, 8, False),
+                rows * 128, rows=rows)
+        for rows, ld, koff in ((6144, 3072, 1024), (8884, 7168, 5120)):   # DiT: RMS norm of q and k inside the packed qkv
+            qkv = torch.randn(rows, ld, device="cuda").half()
+            g64 = torch.randn(64, device="cuda").half()
+            rec("qk_norm_rms_qk", lambda: ops.qk_norm_(qkv, 16, 0, koff, 64, 0, 1e-6, g64, None, g64, None),
+                rows * 2048 * 4, rows=rows, ld=ld)
+        wm = torch.randn(290 * 1024, W, device="cuda").half()
+        bm = torch.randn(290 * 1024, device="cuda").half()
+        vec = torch.randn(2, W, device="cuda").half()
+        om = torch.empty(2, 290 * 1024, device="cuda", dtype=torch.float16)
+        rec("gemv_modulation", lambda: ops.gemv(wm, bm, vec, silu_in=True, out=om), wm.numel() * 2, rows=290 * 1024)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("R3G_MB_OUT", "microbench.json")), "w"), indent=1)
 
