@@ -42,6 +42,10 @@ struct LinearParams {
   const float* ls_gamma;
   int out_f32;
   int tiles_m, tiles_n;
+  // fused per-head q/k normalisation (0 off, 1 RMS, 2 LayerNorm) of the 64-column heads in two column ranges
+  int qkn_mode, qkn_q_col0, qkn_k_col0, qkn_cols;
+  float qkn_eps;
+  const __half *qkn_q_w, *qkn_q_b, *qkn_k_w, *qkn_k_b;
 };
 
 template <int BN>
@@ -175,6 +179,106 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
 
 }
 
+// One 64-column head of one accumulator row with the q/k normalisation fused (qkn_mode): v0 / v1 = the two 32-column
+// accumulator chunks of columns [n0, n0+64).  Same arithmetic as qk_norm_kernel (rowops.cu): the Linear output is an
+// fp16 tensor, the statistics are fp32, RMS: (x * rrms).to(fp16) * scale; LayerNorm: (x - mean) * rstd * w + b.
+__device__ __forceinline__ void epilogue_qknorm(const LinearParams& p, const uint32_t* v0, const uint32_t* v1,
+                                                int64_t out_row, int n0, const __half* nw, const __half* nb) {
+  float f[64];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    f[j] = __uint_as_float(v0[j]);
+    f[32 + j] = __uint_as_float(v1[j]);
+  }
+  if (p.bias) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 b4 = __ldg(bp + q);
+      const __half2* h = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 t = __half22float2(h[j]);
+        f[q * 8 + 2 * j] += t.x;
+        f[q * 8 + 2 * j + 1] += t.y;
+      }
+    }
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; j += 4) {
+    f[j] = __half2float(__float2half_rn(f[j]));
+    f[j + 1] = __half2float(__float2half_rn(f[j + 1]));
+    f[j + 2] = __half2float(__float2half_rn(f[j + 2]));
+    f[j + 3] = __half2float(__float2half_rn(f[j + 3]));
+    if (p.qkn_mode == 1) {
+      s0 = fmaf(f[j], f[j], s0); s1 = fmaf(f[j + 1], f[j + 1], s1);
+      s2 = fmaf(f[j + 2], f[j + 2], s2); s3 = fmaf(f[j + 3], f[j + 3], s3);
+    } else {
+      s0 += f[j]; s1 += f[j + 1]; s2 += f[j + 2]; s3 += f[j + 3];
+    }
+  }
+  if (p.qkn_mode == 1) {
+    const float rrms = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.f / 64.f) + p.qkn_eps);
+    const uint4* wp = reinterpret_cast<const uint4*>(nw);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 w4 = __ldg(wp + q);
+      const __half2* h = reinterpret_cast<const __half2*>(&w4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h[j]);
+        f[q * 8 + 2 * j] = __half2float(__float2half_rn(f[q * 8 + 2 * j] * rrms)) * t.x;
+        f[q * 8 + 2 * j + 1] = __half2float(__float2half_rn(f[q * 8 + 2 * j + 1] * rrms)) * t.y;
+      }
+    }
+  } else {
+    const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / 64.f);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      f[j] -= mean; f[j + 1] -= mean; f[j + 2] -= mean; f[j + 3] -= mean;
+      q0 = fmaf(f[j], f[j], q0); q1 = fmaf(f[j + 1], f[j + 1], q1);
+      q2 = fmaf(f[j + 2], f[j + 2], q2); q3 = fmaf(f[j + 3], f[j + 3], q3);
+    }
+    const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.f / 64.f) + p.qkn_eps);
+    const uint4* wp = reinterpret_cast<const uint4*>(nw);
+    const uint4* bp = reinterpret_cast<const uint4*>(nb);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 w4 = __ldg(wp + q);
+      uint4 b4 = make_uint4(0, 0, 0, 0);
+      if (nb) b4 = __ldg(bp + q);
+      const __half2* hw = reinterpret_cast<const __half2*>(&w4);
+      const __half2* hb = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 tw = __half22float2(hw[j]), tb = __half22float2(hb[j]);
+        f[q * 8 + 2 * j] = f[q * 8 + 2 * j] * rstd * tw.x + tb.x;
+        f[q * 8 + 2 * j + 1] = f[q * 8 + 2 * j + 1] * rstd * tw.y + tb.y;
+      }
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + out_row * p.ldy + n0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 o;
+    o.x = pack_half2(f[8 * q + 0], f[8 * q + 1]);
+    o.y = pack_half2(f[8 * q + 2], f[8 * q + 3]);
+    o.z = pack_half2(f[8 * q + 4], f[8 * q + 5]);
+    o.w = pack_half2(f[8 * q + 6], f[8 * q + 7]);
+    op[q] = o;
+  }
+}
+
+// which normalisation range (0 = q, 1 = k, -1 = none) the 64-column group starting at n0 belongs to
+__device__ __forceinline__ int qkn_range(const LinearParams& p, int n0) {
+  if (!p.qkn_mode) return -1;
+  if (n0 >= p.qkn_q_col0 && n0 < p.qkn_q_col0 + p.qkn_cols) return 0;
+  if (p.qkn_k_col0 >= 0 && n0 >= p.qkn_k_col0 && n0 < p.qkn_k_col0 + p.qkn_cols) return 1;
+  return -1;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -287,6 +391,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0), v);
+        const int nr = (BN >= 128 && (c0 & 32) == 0) ? qkn_range(p, n0) : -1;   // warp-uniform
+        if (nr >= 0) {
+          uint32_t v1[32];
+          tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0 + 32), v1);
+          tmem_ld_wait();
+          if (row_ok) epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b);
+          c0 += 32;
+          continue;
+        }
         tmem_ld_wait();
         if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
       }
@@ -336,6 +449,10 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.residual_f32 = a->residual_f32 ? (const float*)a->residual : nullptr;
   p.ls_gamma = (const float*)a->ls_gamma;
   p.out_f32 = a->out_f32;
+  p.qkn_mode = a->qkn_mode; p.qkn_q_col0 = a->qkn_q_col0; p.qkn_k_col0 = a->qkn_k_col0; p.qkn_cols = a->qkn_cols;
+  p.qkn_eps = a->qkn_eps;
+  p.qkn_q_w = (const __half*)a->qkn_q_w; p.qkn_q_b = (const __half*)a->qkn_q_b;
+  p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
   p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = (a->N + BN - 1) / BN;
   static bool attr_set = false;
@@ -475,6 +592,15 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int n0 = tn * BN2 + c0;
         uint32_t v[32];
         tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN2 + c0), v);
+        const int nr = (c0 & 32) == 0 ? qkn_range(p, n0) : -1;   // warp-uniform
+        if (nr >= 0) {
+          uint32_t v1[32];
+          tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN2 + c0 + 32), v1);
+          tmem_ld_wait();
+          if (row_ok) epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b);
+          c0 += 32;
+          continue;
+        }
         tmem_ld_wait();
         if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
       }
@@ -523,6 +649,10 @@ int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.residual_f32 = a->residual_f32 ? (const float*)a->residual : nullptr;
   p.ls_gamma = (const float*)a->ls_gamma;
   p.out_f32 = a->out_f32;
+  p.qkn_mode = a->qkn_mode; p.qkn_q_col0 = a->qkn_q_col0; p.qkn_k_col0 = a->qkn_k_col0; p.qkn_cols = a->qkn_cols;
+  p.qkn_eps = a->qkn_eps;
+  p.qkn_q_w = (const __half*)a->qkn_q_w; p.qkn_q_b = (const __half*)a->qkn_q_b;
+  p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
   p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = a->N / BN2;
   static bool attr_set = false;
@@ -554,6 +684,18 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
   if (a->gate && (!a->residual || a->gate_ld % 8)) return r3g_fail(ctx, R3G_E_INVALID, "linear: gate needs residual");
   if (a->act && (a->act_col0 % 32 || a->act_col1 % 32))
     return r3g_fail(ctx, R3G_E_INVALID, "linear: activation column range must be aligned to 32 columns");
+  if (a->qkn_mode) {
+    const bool k_on = a->qkn_k_col0 >= 0;
+    if (a->qkn_mode < 0 || a->qkn_mode > 2 || a->N < 128 || a->qkn_cols <= 0 || a->qkn_cols % 64 || a->qkn_q_col0 % 64 ||
+        (k_on && a->qkn_k_col0 % 64) || a->qkn_q_col0 < 0 || a->qkn_q_col0 + a->qkn_cols > a->N ||
+        (k_on && a->qkn_k_col0 + a->qkn_cols > a->N) || !a->qkn_q_w || (k_on && !a->qkn_k_w))
+      return r3g_fail(ctx, R3G_E_INVALID, "linear: qkn ranges must be 64-column aligned inside [0, N), N >= 128, weights set");
+    if (a->residual || a->out_f32)
+      return r3g_fail(ctx, R3G_E_INVALID, "linear: the fused q/k normalisation takes a plain fp16 output (no residual)");
+    auto overlaps = [&](int c0) { return a->act && c0 < a->act_col1 && c0 + a->qkn_cols > a->act_col0; };
+    if (overlaps(a->qkn_q_col0) || (k_on && overlaps(a->qkn_k_col0)))
+      return r3g_fail(ctx, R3G_E_INVALID, "linear: normalised columns must lie outside the activation range");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   // Tile choice: wave efficiency (tiles / (waves * units)) times a per-tile throughput factor measured on B200
   // (CTA-pair 256x256: 1.08 for K <= 2048 else 0.93, 128x256: 1.0, 128x128: 0.7).  N = 1024 GEMMs with ~6k rows, for example, fill only

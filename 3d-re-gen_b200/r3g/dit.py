@@ -48,6 +48,8 @@ class Hunyuan3DDiT:
         self.w = None
         self._ws = {}
         self.taps = None  # set to a list to record the hidden state after every block (parity tests)
+        # QKNorm inside the q/k/v projection's epilogue (r3g_linear qkn_*); False runs the separate r3g_qk_norm pass
+        self.fuse_qk_norm = True
 
     # ------------------------------------------------------------------------------------------ weights
     def to(self, device=None, dtype=None):
@@ -199,9 +201,13 @@ class Hunyuan3DDiT:
                 xm = XM[:, ofs:ofs + Ls]
                 ops.layernorm(xs, eps=1e-6, scale=sc1, shift=sh1, rows_per_batch=Ls, out=xm)
                 qkv_s = QKV[:, ofs:ofs + Ls]
-                ops.linear(xm, w[p + f"{s}_attn.qkv.weight"], w[p + f"{s}_attn.qkv.bias"], out=qkv_s)
-                ops.qk_norm_(qkv_s, nh, 0, H, 64, 0, 1e-6, w[p + f"{s}_attn.norm.query_norm.scale"], None,
-                             w[p + f"{s}_attn.norm.key_norm.scale"], None)
+                qs, ks = w[p + f"{s}_attn.norm.query_norm.scale"], w[p + f"{s}_attn.norm.key_norm.scale"]
+                if self.fuse_qk_norm:
+                    ops.linear(xm, w[p + f"{s}_attn.qkv.weight"], w[p + f"{s}_attn.qkv.bias"], out=qkv_s,
+                               qk_norm=dict(mode=ops.QKN_RMS, q_col0=0, k_col0=H, cols=H, eps=1e-6, q_w=qs, k_w=ks))
+                else:
+                    ops.linear(xm, w[p + f"{s}_attn.qkv.weight"], w[p + f"{s}_attn.qkv.bias"], out=qkv_s)
+                    ops.qk_norm_(qkv_s, nh, 0, H, 64, 0, 1e-6, qs, None, ks, None)
             ops.attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], out=q4[:, :, 0])  # joint txt+img attention
             for s, xs, ofs, Ls in (("img", img, Lt, Li), ("txt", txt, 0, Lt)):
                 sh1, sc1, g1, sh2, sc2, g2 = self._mod(ws, (i, s), 6)
@@ -224,10 +230,15 @@ class Hunyuan3DDiT:
             p = f"single_blocks.{i}."
             shift, scale, gate = self._mod(ws, ("s", i), 3)
             ops.layernorm(X, eps=1e-6, scale=scale, shift=shift, rows_per_batch=L, out=XM)
-            ops.linear(XM, w[p + "linear1.weight"], w[p + "linear1.bias"], out=S1, act=ops.ACT_GELU_TANH,
-                       act_cols=(H, H + Mh))
-            ops.qk_norm_(S1, nh, 0, H + Mh, 64, 0, 1e-6, w[p + "norm.query_norm.scale"], None,
-                         w[p + "norm.key_norm.scale"], None)
+            qs, ks = w[p + "norm.query_norm.scale"], w[p + "norm.key_norm.scale"]
+            if self.fuse_qk_norm:
+                ops.linear(XM, w[p + "linear1.weight"], w[p + "linear1.bias"], out=S1, act=ops.ACT_GELU_TANH,
+                           act_cols=(H, H + Mh),
+                           qk_norm=dict(mode=ops.QKN_RMS, q_col0=0, k_col0=H + Mh, cols=H, eps=1e-6, q_w=qs, k_w=ks))
+            else:
+                ops.linear(XM, w[p + "linear1.weight"], w[p + "linear1.bias"], out=S1, act=ops.ACT_GELU_TANH,
+                           act_cols=(H, H + Mh))
+                ops.qk_norm_(S1, nh, 0, H + Mh, 64, 0, 1e-6, qs, None, ks, None)
             ops.attention(s1q, s1k, s1v, out=s1q)
             ops.linear(S1[:, :, :H + Mh], w[p + "linear2.weight"], w[p + "linear2.bias"], out=X, gate=gate,
                        gate_rows=L, residual=X)

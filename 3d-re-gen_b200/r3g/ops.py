@@ -68,13 +68,18 @@ def _merge_seg(xs, ys, name):
     return L, (xst if xl else L), (yst if yl else L)
 
 
+QKN_RMS, QKN_LAYERNORM = 1, 2
+
+
 def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
-           ls_gamma=None, out_dtype=torch.float16):
+           ls_gamma=None, out_dtype=torch.float16, qk_norm=None):
     """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
 
     x: [..., K] or a strided [M, K] / [S, L, K] view, w: [N, K] contiguous, out: same row structure, width N.
     gate: [B, N] view with unit inner stride, applied to logical rows b = r // gate_rows.
     residual must be the same view geometry as out (and may be out itself).
+    qk_norm: dict(mode=QKN_RMS|QKN_LAYERNORM, q_col0, k_col0 (None: q only), cols, eps, q_w, q_b, k_w, k_b) -- the per-head
+    q/k normalisation fused into the epilogue (see qkn_* in include/r3g.h).
     """
     _f16(x, "x"); _f16(w, "w")
     ctx = _ctx(x)
@@ -112,6 +117,17 @@ def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None,
             raise ValueError("residual must share out's geometry")
         a.residual = r2.data_ptr()
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if qk_norm is not None:
+        a.qkn_mode, a.qkn_q_col0, a.qkn_cols = qk_norm["mode"], qk_norm["q_col0"], qk_norm["cols"]
+        a.qkn_k_col0 = qk_norm["k_col0"] if qk_norm.get("k_col0") is not None else -1
+        a.qkn_eps = float(qk_norm["eps"])
+        for name in ("q_w", "q_b", "k_w", "k_b"):
+            t = qk_norm.get(name)
+            if t is not None:
+                _f16(t, name)
+                if t.numel() != 64 or not t.is_contiguous():
+                    raise ValueError(f"qk_norm {name} must be a contiguous fp16 [64]")
+                setattr(a, "qkn_" + name, t.data_ptr())
     ctx.check(ctx.lib.r3g_linear(ctx.handle, C.byref(a), _stream()))
     return out
 

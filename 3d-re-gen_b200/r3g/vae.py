@@ -102,9 +102,12 @@ class CrossAttentionDecoder:
         emb, x, xn, q, h = (ws[k_][:n] for k_ in ("emb", "x", "xn", "q", "h"))
         ops.linear(emb, w["query_proj.weight"], w["query_proj.bias"], out=x)
         ops.layernorm(x, w["ln_1.weight"], w["ln_1.bias"], eps=1e-6, out=xn)
-        ops.linear(xn, w["c_q.weight"], w["c_q.bias"], out=q)
-        if self.qk_norm:
-            ops.qk_norm_(q, nh, 0, 0, 64, 1, 1e-6, w["q_norm.weight"], w["q_norm.bias"])
+        if self.qk_norm:   # per-head LayerNorm of q inside the projection's epilogue
+            ops.linear(xn, w["c_q.weight"], w["c_q.bias"], out=q,
+                       qk_norm=dict(mode=ops.QKN_LAYERNORM, q_col0=0, k_col0=None, cols=W, eps=1e-6,
+                                    q_w=w["q_norm.weight"], q_b=w["q_norm.bias"]))
+        else:
+            ops.linear(xn, w["c_q.weight"], w["c_q.bias"], out=q)
         q4 = q.view(1, n, nh, 64)
         ops.attention(q4, k, v, out=q4)
         ops.linear(q, w["c_proj.weight"], w["c_proj.bias"], out=x, residual=x)

@@ -85,6 +85,13 @@ int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, flo
  *   residual_f32 / ls_gamma: the VGGT block form (vggt/layers/block.py:77-98 under autocast): the residual stream is
  *        float32, `residual` then points to float32 with Y's geometry (Y float32, may alias), and
  *        Y = residual + ls_gamma[n] * fp16(acc + bias)  with ls_gamma the float32 LayerScale vector (NULL = 1).
+ *   qkn_*: the per-head q/k normalisation that follows a q/k/v projection, fused into the epilogue (the accumulator
+ *        row of a 64-column head sits in one thread's registers): qkn_mode 1 = RMSNorm(64) with a learned scale
+ *        (QKNorm, hunyuan3ddit.py:83-104,199,260), 2 = LayerNorm(64) with weight + bias (attention_blocks.py:315-316,
+ *        250-258).  It is applied to the fp16-rounded Linear output of the 64-column heads in
+ *        [qkn_q_col0, qkn_q_col0 + qkn_cols) with (qkn_q_w, qkn_q_b) and, if qkn_k_col0 >= 0, of
+ *        [qkn_k_col0, qkn_k_col0 + qkn_cols) with (qkn_k_w, qkn_k_b); the weights are fp16 [64] (bias NULL in mode 1).
+ *        Column offsets and qkn_cols are multiples of 64; these columns must carry no activation / gate / residual.
  */
 typedef struct {
   const void* x; int64_t ldx;
@@ -99,6 +106,9 @@ typedef struct {
   int out_f32;
   int residual_f32;
   const void* ls_gamma;      /* float32 [N] or NULL */
+  int qkn_mode, qkn_q_col0, qkn_k_col0, qkn_cols;
+  float qkn_eps;
+  const void* qkn_q_w; const void* qkn_q_b; const void* qkn_k_w; const void* qkn_k_b;
 } r3g_linear_args;
 int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream);
 

@@ -102,3 +102,46 @@ def test_attention_packed_qkv_in_place():
     ref2 = F.scaled_dot_product_attention(q2.float().transpose(1, 2), k2.float().transpose(1, 2),
                                           v2.float().transpose(1, 2)).transpose(1, 2)
     assert (ops.attention(q2, k2, v2).float() - ref2).abs().max().item() < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 384, 256, False), (1000, 3072, 1024, False), (777, 7168, 512, True)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_linear_fused_qk_norm(M, N, K, act, mode):
+    """The q/k normalisation inside the GEMM epilogue (qkn_*) against the separate r3g_qk_norm pass and against torch:
+    RMSNorm / LayerNorm over each 64-column head of the fp16 Linear output (hunyuan3ddit.py:83-104,
+    attention_blocks.py:315-316)."""
+    from r3g import ops
+    torch.manual_seed(5)
+    x = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+    b = torch.randn(N, device="cuda").half()
+    qw, kw = (1 + 0.1 * torch.randn(64, device="cuda")).half(), (1 + 0.1 * torch.randn(64, device="cuda")).half()
+    qb, kb = (0.1 * torch.randn(64, device="cuda")).half(), (0.1 * torch.randn(64, device="cuda")).half()
+    cols = 128 if N < 1024 else 1024
+    q0, k0 = 0, N - 2 * cols if act else cols
+    kw_act = dict(act=ops.ACT_GELU_TANH, act_cols=(cols, N - 2 * cols)) if act else {}
+    qk = dict(mode=mode, q_col0=q0, k_col0=k0, cols=cols, eps=1e-6, q_w=qw, k_w=kw)
+    if mode == 2:
+        qk.update(q_b=qb, k_b=kb)
+    fused = ops.linear(x, w, b, qk_norm=qk, **kw_act)
+    plain = ops.linear(x, w, b, **kw_act)
+    two_pass = plain.clone()
+    ops.qk_norm_(two_pass, cols // 64, q0, k0, 64, mode - 1, 1e-6, qw, qb if mode == 2 else None, kw,
+                 kb if mode == 2 else None)
+    # torch reference on the fp16 Linear output
+    ref = plain.float().clone()
+    for c0, wv, bv in ((q0, qw, qb), (k0, kw, kb)):
+        h = plain[:, c0:c0 + cols].float().view(M, cols // 64, 64)
+        if mode == 1:
+            rr = torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + 1e-6)
+            y = (h * rr).half().float() * wv.float()
+        else:
+            y = F.layer_norm(h, (64,), wv.float(), bv.float(), 1e-6)
+        ref[:, c0:c0 + cols] = y.reshape(M, cols)
+    untouched = torch.ones(N, dtype=torch.bool, device="cuda")
+    untouched[q0:q0 + cols] = False
+    untouched[k0:k0 + cols] = False
+    assert torch.equal(fused[:, untouched], plain[:, untouched])          # other columns: the ordinary epilogue
+    d = (fused.float() - two_pass.float()).abs()
+    assert d.max().item() <= 4e-3 and (d > 0).float().mean().item() < 0.02  # fp32 sum order only: rare 1-ulp flips
+    assert (fused.float() - ref).abs().max().item() <= 6e-3
