@@ -55,7 +55,8 @@ struct Cfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    kNumEpilogueWarps * 768 /*epilogue operand slices*/;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -91,17 +92,55 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;   // x>0: 0.5x(1+erf), x<0: 0.5x(1-erf|.|)
 }
 
+// Epilogue operands.  The epilogue warps (two per scheduler) cannot hide an L2 round trip per 32-column chunk: the
+// first version loaded bias / gate / residual after tcgen05.wait::ld and 48 % of the kernel's stall samples sat on
+// those loads (profiles/README.md r1f).  Now each epilogue warp stages its 128-column slice of the bias row and of
+// the (at most two) gate rows its 32 rows can belong to in its own 768 bytes of shared memory while it waits for the
+// accumulator, and the fp16 residual -- the only per-thread operand -- is fetched one chunk ahead of its use.
+constexpr int kEpiSmemPerWarp = 768;   // uint4 [0,16) bias, [16,32) gate row of lane 0's batch, [32,48) of lane 31's
+struct ChunkOperands {
+  uint4 res[4];
+};
+__device__ __forceinline__ void prefetch_residual(const LinearParams& p, int64_t out_row, int n0, ChunkOperands& o) {
+  if (p.residual) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldy + n0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.res[q] = rp[q];
+  }
+}
+// stage this warp's bias / gate slices for the tile (columns [ncol0, ncol0 + ncols)); returns this lane's gate slice
+// selector (0 / 1) or -1 when gates are read from global memory (gate_rows < 64: more than two batches per warp)
+__device__ __forceinline__ int stage_tile_operands(const LinearParams& p, uint4* wsm, int lane, int ncol0, int ncols,
+                                                   int r_lane0, int r_lane31, int r_mine) {
+  __syncwarp();   // the previous tile's readers are done
+  const bool in = lane < ncols / 8 && ncol0 + lane * 8 < p.N;
+  int sel = -1;
+  if (p.bias && in) wsm[lane] = __ldg(reinterpret_cast<const uint4*>(p.bias + ncol0) + lane);
+  if (p.gate && p.gate_rows >= 64) {
+    const int b_lo = r_lane0 / p.gate_rows, b_hi = r_lane31 / p.gate_rows;
+    if (in) {
+      wsm[16 + lane] = __ldg(reinterpret_cast<const uint4*>(p.gate + (int64_t)b_lo * p.gate_ld + ncol0) + lane);
+      wsm[32 + lane] = __ldg(reinterpret_cast<const uint4*>(p.gate + (int64_t)b_hi * p.gate_ld + ncol0) + lane);
+    }
+    sel = r_mine / p.gate_rows - b_lo;
+  }
+  __syncwarp();
+  return sel;
+}
+
 // One 32-column chunk of one accumulator row: v = fp32 accumulators of columns [n0, n0+32) of logical row r.
+// sbias / sgate: this chunk's 4 uint4 of the staged slices (sgate NULL: gate from global memory or no gate);
+// `pre` holds this chunk's residual and is refilled for chunk next_n0 (>= 0) as soon as it has been consumed.
 __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint32_t* v, int r, int64_t out_row,
-                                               int n0, const __half* gate_row) {
+                                               int n0, const uint4* sbias, const uint4* sgate, const __half* gate_row,
+                                               ChunkOperands& pre, int next_n0) {
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     if (p.bias) {
-      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 b4 = __ldg(bp + q);
+        const uint4 b4 = sbias[q];
         const __half2* h = reinterpret_cast<const __half2*>(&b4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -123,13 +162,13 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
       }
     }
     if (p.residual) {
-      const __half* rp = p.residual + out_row * p.ldy + n0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 r4 = *reinterpret_cast<const uint4*>(rp + 8 * q);
+        const uint4 r4 = pre.res[q];
         const __half2* h = reinterpret_cast<const __half2*>(&r4);
         uint4 g4 = make_uint4(0, 0, 0, 0);
-        if (gate_row) g4 = __ldg(reinterpret_cast<const uint4*>(gate_row + n0) + q);
+        if (sgate) g4 = sgate[q];
+        else if (gate_row) g4 = __ldg(reinterpret_cast<const uint4*>(gate_row + n0) + q);
         const __half2* gh = reinterpret_cast<const __half2*>(&g4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -145,6 +184,7 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
           f[q * 8 + 2 * j + 1] = rr.y + y1;
         }
       }
+      if (next_n0 >= 0) prefetch_residual(p, out_row, next_n0, pre);
     }
     if (p.residual_f32) {
       const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + out_row * p.ldy + n0);
@@ -183,7 +223,8 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
 // accumulator chunks of columns [n0, n0+64).  Same arithmetic as qk_norm_kernel (rowops.cu): the Linear output is an
 // fp16 tensor, the statistics are fp32, RMS: (x * rrms).to(fp16) * scale; LayerNorm: (x - mean) * rstd * w + b.
 __device__ __forceinline__ void epilogue_qknorm(const LinearParams& p, const uint32_t* v0, const uint32_t* v1,
-                                                int64_t out_row, int n0, const __half* nw, const __half* nb) {
+                                                int64_t out_row, int n0, const __half* nw, const __half* nb,
+                                                const uint4* sbias8) {
   float f[64];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -191,10 +232,9 @@ __device__ __forceinline__ void epilogue_qknorm(const LinearParams& p, const uin
     f[32 + j] = __uint_as_float(v1[j]);
   }
   if (p.bias) {
-    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      uint4 b4 = __ldg(bp + q);
+      const uint4 b4 = sbias8[q];
       const __half2* h = reinterpret_cast<const __half2*>(&b4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -292,6 +332,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + C::kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + C::kStages * C::kStageBytes + 256;   // per-epilogue-warp operand slices
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -372,23 +413,34 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int col_half = (warp - 2) >> 2;    // which half of the tile's columns this warp owns
     const int row_in_tile = quad * 32 + lane;
+    uint4* wsm = reinterpret_cast<uint4*>(epi_smem + (warp - 2) * kEpiSmemPerWarp);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int sg = tm / p.tiles_per_seg;
       const int l = (tm % p.tiles_per_seg) * BM + row_in_tile;  // row inside the segment
       const bool row_ok = l < p.seg_len;
       const int r = sg * p.seg_len + l;                          // logical row
       const int64_t out_row = (int64_t)sg * p.y_seg_stride + l;
       const __half* gate_row = p.gate ? p.gate + (int64_t)(row_ok ? r / p.gate_rows : 0) * p.gate_ld : nullptr;
+      // stage the warp's bias / gate slices while the accumulator is still being produced
+      const int l0 = l - lane, l31 = min(l0 + 31, p.seg_len - 1);
+      const int ncol0 = tn * BN + col_half * (BN / 2);
+      int gsel = -1;
+      if (l0 < p.seg_len)
+        gsel = stage_tile_operands(p, wsm, lane, ncol0, BN / 2, sg * p.seg_len + l0, sg * p.seg_len + l31,
+                                   row_ok ? r : sg * p.seg_len + l31);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      ChunkOperands pre;
+      bool have_pre = false;
 #pragma unroll 1
       for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
         const int n0 = tn * BN + c0;
         if (n0 >= p.N) break;  // warp-uniform
+        const uint4* sbias = wsm + ((c0 - col_half * (BN / 2)) >> 3);
         uint32_t v[32];
         tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0), v);
         const int nr = (BN >= 128 && (c0 & 32) == 0) ? qkn_range(p, n0) : -1;   // warp-uniform
@@ -396,12 +448,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
           uint32_t v1[32];
           tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN + c0 + 32), v1);
           tmem_ld_wait();
-          if (row_ok) epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b);
+          if (row_ok)
+            epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b, sbias);
           c0 += 32;
+          have_pre = false;
           continue;
         }
+        if (!have_pre && row_ok) prefetch_residual(p, out_row, n0, pre);
+        const int c1 = c0 + 32;   // the next chunk of this warp's column half, if it is an ordinary one
+        const bool more = c1 < (col_half + 1) * (BN / 2) && tn * BN + c1 < p.N &&
+                          !(BN >= 128 && (c1 & 32) == 0 && qkn_range(p, tn * BN + c1) >= 0);
         tmem_ld_wait();
-        if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
+        if (row_ok)
+          epilogue_chunk(p, v, r, out_row, n0, sbias, gsel >= 0 ? sbias + 16 + 16 * gsel : nullptr, gate_row, pre,
+                         more ? tn * BN + c1 : -1);
+        have_pre = more;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -476,7 +537,7 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
 // what bounds that kernel (12 TB/s of L2 bandwidth at 1.0 PFLOP/s), and room for a 6-deep ring.
 constexpr int kStages2 = 6;
 constexpr int kStageBytes2 = BM * BK * 2 + 128 * BK * 2;       // 16 KB of X + 16 KB of W per CTA
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kNumEpilogueWarps * 768;
 constexpr int BN2 = 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
@@ -489,6 +550,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint64_t* tmem_full_bar = empty_bar + kStages2;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (leader's copy is the one the MMA warp waits on)
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + kStages2 * kStageBytes2 + 256;   // per-epilogue-warp operand slices
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -574,35 +636,56 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int quad = warp & 3;
     const int col_half = (warp - 2) >> 2;
     const int row_in_tile = (int)cta_rank * BM + quad * 32 + lane;
+    uint4* wsm = reinterpret_cast<uint4*>(epi_smem + (warp - 2) * kEpiSmemPerWarp);
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int sg = tm / p.tiles_per_seg;
-      const int l = (tm % p.tiles_per_seg) * 256 + row_in_tile;
+      const int l = (tm % p.tiles_per_seg) * 256 + row_in_tile;  // row inside the segment
       const bool row_ok = l < p.seg_len;
-      const int r = sg * p.seg_len + l;
+      const int r = sg * p.seg_len + l;                          // logical row
       const int64_t out_row = (int64_t)sg * p.y_seg_stride + l;
       const __half* gate_row = p.gate ? p.gate + (int64_t)(row_ok ? r / p.gate_rows : 0) * p.gate_ld : nullptr;
+      // stage the warp's bias / gate slices while the accumulator is still being produced
+      const int l0 = l - lane, l31 = min(l0 + 31, p.seg_len - 1);
+      const int ncol0 = tn * BN2 + col_half * (BN2 / 2);
+      int gsel = -1;
+      if (l0 < p.seg_len)
+        gsel = stage_tile_operands(p, wsm, lane, ncol0, BN2 / 2, sg * p.seg_len + l0, sg * p.seg_len + l31,
+                                   row_ok ? r : sg * p.seg_len + l31);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      ChunkOperands pre;
+      bool have_pre = false;
 #pragma unroll 1
       for (int c0 = col_half * (BN2 / 2); c0 < (col_half + 1) * (BN2 / 2); c0 += 32) {
         const int n0 = tn * BN2 + c0;
+        if (n0 >= p.N) break;  // warp-uniform
+        const uint4* sbias = wsm + ((c0 - col_half * (BN2 / 2)) >> 3);
         uint32_t v[32];
         tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN2 + c0), v);
-        const int nr = (c0 & 32) == 0 ? qkn_range(p, n0) : -1;   // warp-uniform
+        const int nr = (BN2 >= 128 && (c0 & 32) == 0) ? qkn_range(p, n0) : -1;   // warp-uniform
         if (nr >= 0) {
           uint32_t v1[32];
           tmem_ld32(tmem_addr(tmem_base, quad * 32, acc * BN2 + c0 + 32), v1);
           tmem_ld_wait();
-          if (row_ok) epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b);
+          if (row_ok)
+            epilogue_qknorm(p, v, v1, out_row, n0, nr ? p.qkn_k_w : p.qkn_q_w, nr ? p.qkn_k_b : p.qkn_q_b, sbias);
           c0 += 32;
+          have_pre = false;
           continue;
         }
+        if (!have_pre && row_ok) prefetch_residual(p, out_row, n0, pre);
+        const int c1 = c0 + 32;   // the next chunk of this warp's column half, if it is an ordinary one
+        const bool more = c1 < (col_half + 1) * (BN2 / 2) && tn * BN2 + c1 < p.N &&
+                          !(BN2 >= 128 && (c1 & 32) == 0 && qkn_range(p, tn * BN2 + c1) >= 0);
         tmem_ld_wait();
-        if (row_ok) epilogue_chunk(p, v, r, out_row, n0, gate_row);
+        if (row_ok)
+          epilogue_chunk(p, v, r, out_row, n0, sbias, gsel >= 0 ? sbias + 16 + 16 * gsel : nullptr, gate_row, pre,
+                         more ? tn * BN2 + c1 : -1);
+        have_pre = more;
       }
       tc_fence_before();
       __syncwarp();
