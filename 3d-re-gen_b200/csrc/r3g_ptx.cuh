@@ -196,6 +196,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// The same, multicast: the box lands at the same smem offset of every CTA in `mask` and each destination's bytes are
+// signalled on the mbarrier of ITS pair leader (the peer-bit trick applies per destination CTA).
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                   uint16_t mask, uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 // arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of the cluster.  RELAXED: the callers order
 // their TMEM accesses with tcgen05 fences; a .release.cluster arrive compiles to MEMBAR.ALL.GPU (microseconds).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
