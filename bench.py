@@ -174,7 +174,13 @@ def instrumented_linear_roofline(pipe, cond, peak_tflops):
             "launches_timed": len(calls), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": None, "avg_launch_ms": ms / len(calls),
             "flops_per_launch_avg": flops / len(calls),
-            "note": "weights stream from HBM (2.2 GB per forward > L2); activations mostly L2-resident"}
+            "note": "weights stream from HBM (2.2 GB per forward > L2); activations mostly L2-resident",
+            # not measured in this run: DRAM bytes of the largest of these launches from the committed ncu --set full
+            # capture (dram__bytes_read.sum + dram__bytes_write.sum); `traffic` stays null because the live figure above
+            # averages 195 launches of 10 different shapes
+            "traffic_ncu": {"launch": "single-block linear1 8884x7168x1024 (GELU + q/k norm epilogue)",
+                            "dram_bytes": 115.5e6, "algorithmic_bytes": 160.3e6,
+                            "source": "profiles/r1f_ncu_gemm_selected_metrics.txt"}}
 
 
 def main():
