@@ -333,24 +333,6 @@ __device__ __forceinline__ float exp2_poly(float x) {
 }
 // Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issued instruction, operands in
 // aligned 64-bit register pairs -- the S row arrives from tcgen05.ld already laid out that way).
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 // exp2_poly on a pair: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 IMAD for two results
 __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float& e1) {
   const uint64_t x = f2_pack(fmaxf(x0, -30.f), fmaxf(x1, -30.f));

@@ -5,6 +5,9 @@
 #include <math.h>
 
 #include "r3g_internal.h"
+#include "r3g_ptx.cuh"
+
+using namespace r3g;
 
 namespace {
 
@@ -44,29 +47,6 @@ constexpr int kLnMaxChunks = 8;  // 8 chunks * 32 lanes * 8 halfs = 2048
 // two IEEE fp32 results per instruction) and the affine weights sit in shared memory as fp32: at 6.5 TB/s an fp16
 // LayerNorm has a budget of ~10 issue slots per element, the scalar version spent 11 and ran at 2.6 TB/s
 // (profiles/README.md r1f).
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ uint32_t f2_to_h2(uint64_t v) {   // round a pair to packed fp16 (lo in the low half)
   float lo, hi;
   f2_unpack(v, lo, hi);

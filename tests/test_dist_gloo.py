@@ -32,7 +32,9 @@ def _worker(rank, world, port, q):
                                                                         dtype=torch.int32)))
     got = gather_meshes(meshes)
     if rank == 0:
-        q.put((mine, [(v.clone(), f.clone()) for v, f in got]))
+        # plain numpy through the queue: torch tensors travel as shared-memory file descriptors that the parent has to
+        # fetch from THIS process, which may already have exited (ConnectionResetError in a slow parent)
+        q.put((mine, [(v.numpy().copy(), f.numpy().copy()) for v, f in got]))
     else:
         q.put((mine, len(got)))
     # a rank with nothing to send must not deadlock the gather
@@ -43,17 +45,26 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_shard_and_gather_world2():
+def _run_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    try:
+        res = [q.get(timeout=120) for _ in range(2)]
+    except Exception:
+        res = None
     for p in procs:
         p.join(timeout=120)
-        assert p.exitcode == 0
+    return res if res is not None and all(p.exitcode == 0 for p in procs) else None
+
+
+def test_shard_and_gather_world2():
+    # the TCP rendezvous on a just-released port can be reset on a loaded box: one retry on a fresh port
+    res = _run_world2() or _run_world2()
+    assert res is not None, "world-size-2 gloo run failed twice"
     r0 = [r for r in res if isinstance(r[1], list)][0]
     r1 = [r for r in res if not isinstance(r[1], list)][0]
     assert r0[0] == [0, 2, 4, 6] and r1[0] == [1, 3, 5] and r1[1] == 0
@@ -63,7 +74,7 @@ def test_shard_and_gather_world2():
         g = torch.Generator().manual_seed(i)
         ev = torch.rand(i + 1, 3, generator=g)
         ef = torch.randint(0, i + 1, (2 * i + 1, 3), generator=g, dtype=torch.int32)
-        assert torch.equal(v, ev) and torch.equal(f, ef)
+        assert torch.equal(torch.from_numpy(v), ev) and torch.equal(torch.from_numpy(f), ef)
 
 
 def test_single_process_passthrough():
