@@ -77,3 +77,21 @@ def test_stage3_twin_file_contract(tmp_path, monkeypatch):
     cfg = tmp_path / "c.yaml"
     cfg.write_text("num_inf_steps_hy: 50\noctree_resolution_hy: 256\nuse_banana: false\n")
     assert run.load_config(str(cfg))["octree_resolution_hy"] == 256
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port on the host cores) prints one JSON line with the contract's keys;
+    under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "objects/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("objects->mesh/sec") and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
