@@ -681,7 +681,7 @@ constexpr uint32_t kTmemP = 192;
 // kF32: exponentials as scalar ex2.approx.f32 packed afterwards (2 FFMA + 2 MUFU + 1 F2FP per pair) instead of
 // ex2.approx.f16x2, which ptxas splits into 2 MUFU.EX2.F16 + a PRMT on top of the F2FP that feeds it.
 // kPoly: every kPoly-th pair of exponentials runs on the FMA pipe (0 = none).
-template <bool kPT, bool kF32, int kPoly>
+template <bool kPT, bool kF32, int kPoly, bool kF2 = false>
 __global__ void __launch_bounds__(kThreadsV3, 2)
 attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -856,19 +856,32 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       float rs = 0.f;
       uint32_t carry = 0;
+      const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(-m_used, -m_used);
       uint32_t pk[kHalf / 2];
 #pragma unroll
       for (int c = 0; c < kHalf; c += 16) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          const float x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
-          const float x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
-          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1)
-            pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
-          else if (kF32)
+          float x0, x1;
+          if (kF2) {
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 1])), scale2, nm2), x0, x1);
+          } else {
+            x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
+            x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
+          }
+          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1) {
+            if (kF2) {
+              float e0, e1;
+              exp2_poly2(x0, x1, e0, e1);
+              pk[(c + i) >> 1] = cvt_f16x2(e0, e1);
+            } else {
+              pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
+            }
+          } else if (kF32) {
             pk[(c + i) >> 1] = cvt_f16x2(ex2(x0), ex2(x1));
-          else
+          } else {
             pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(x0, x1));
+          }
         }
         const uint32_t* q8 = &pk[c >> 1];
         const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
@@ -945,9 +958,11 @@ using AttnKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensor
 // Kernel generations kept for the parity tests and A/B runs (R3G_ATTN = family, R3G_ATTN_VARIANT = index):
 //   family 2 (one thread per row, the default): [0] as measured at r1c (P through shared memory, ex2.f16x2),
 //                                               [1] the default: P in TMEM, f32 exps, packed-fp32 softmax, 1/4 poly
-//   family 3 (two threads per row):             [0] as measured at r1d, [1] P in TMEM + f32 exps + 1/6 poly
+//   family 3 (two threads per row):             [0] as measured at r1d, [1] P in TMEM + f32 exps + 1/6 poly,
+//                                               [2] / [3] the same with the packed-fp32 softmax and 1/4 / 1/3 poly
 // The sweep over the other combinations (runs 16-23) is recorded in profiles/README.md.
-const AttnKernel kV3Variants[] = {attention_kernel_v3<false, false, 4>, attention_kernel_v3<true, true, 6>};
+const AttnKernel kV3Variants[] = {attention_kernel_v3<false, false, 4>, attention_kernel_v3<true, true, 6>,
+                                  attention_kernel_v3<true, true, 4, true>, attention_kernel_v3<true, true, 3, true>};
 const AttnKernel kV2Variants[] = {attention_kernel<false, false, 0, 2>, attention_kernel<true, true, 4, 2, true>};
 
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
