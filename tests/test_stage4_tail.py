@@ -178,3 +178,31 @@ def test_sparse_model_and_camera_export_end_to_end(tmp_path):
     Rp, Tp = stage4.B2P(z["extrinsic"])
     exp = ((p0 @ R_fix.T) @ Rp.T + Tp) * np.array([1, -1, 1]) * 5.0
     assert np.allclose(stage4.read_ply_vertices(cfg["vggt_cloud"]), exp, atol=1e-4)
+
+
+def test_image_loader_against_the_reference_when_available(tmp_path):
+    """Row v1: load_and_preprocess_images_square (vggt/vggt/utils/load_fn.py:13-94) -- RGBA on white, centre padding to a
+    black square, PIL bicubic resize, ToTensor -- and the original-coordinate table the rescale step consumes."""
+    ref = "/root/reference/vggt/vggt/utils/load_fn.py"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference not present")
+    import importlib.util
+    import torch
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("_ref_load_fn", ref)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(9)
+    paths = []
+    for i, (w, h, mode) in enumerate(((150, 100, "RGB"), (64, 97, "RGBA"), (80, 80, "RGB"))):
+        arr = rng.integers(0, 256, (h, w, 4 if mode == "RGBA" else 3)).astype(np.uint8)
+        pth = tmp_path / f"im{i}.png"
+        Image.fromarray(arr, mode).save(pth)
+        paths.append(str(pth))
+    for sel in (paths, paths[:1]):
+        a_img, a_xy = stage4.load_and_preprocess_images_square(sel, 256)
+        b_img, b_xy = m.load_and_preprocess_images_square(sel, 256)
+        assert a_img.shape == b_img.shape and torch.equal(a_img, b_img)
+        assert torch.equal(a_xy, b_xy)
+    with pytest.raises(ValueError):
+        stage4.load_and_preprocess_images_square([], 256)
