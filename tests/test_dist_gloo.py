@@ -83,3 +83,21 @@ def test_single_process_passthrough():
     assert shard_indices(5, 1, 3) == [1, 4]
     m = [(torch.rand(4, 3), torch.zeros(2, 3, dtype=torch.int32))]
     assert gather_meshes(m)[0][0] is m[0][0]
+
+
+def test_shard_indices_partition_property():
+    """Every object index is owned by exactly one rank, in increasing order per rank, for any (n, world)."""
+    sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
+    from hypothesis import given, settings, strategies as st
+    from r3g.dist import shard_indices
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 200), st.integers(1, 16))
+    def check(n, world):
+        seen = []
+        for r in range(world):
+            mine = shard_indices(n, r, world)
+            assert mine == sorted(mine) and all(i % world == r for i in mine)
+            seen += mine
+        assert sorted(seen) == list(range(n))
+    check()
