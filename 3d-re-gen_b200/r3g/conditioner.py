@@ -32,12 +32,12 @@ class DinoImageEncoder:
         """Resize(518, bilinear, antialias) + CenterCrop(518) + Normalize (conditioner.py:78-88)."""
         s = self.image_size
         h, w = image.shape[-2:]
-        if h <= w:
-            nh, nw = s, int(round(s * w / h))
+        if h <= w:   # torchvision's Resize(int): short edge -> s, long edge -> int(s * long / short) (truncated)
+            nh, nw = s, int(s * w / h)
         else:
-            nh, nw = int(round(s * h / w)), s
+            nh, nw = int(s * h / w), s
         image = F.interpolate(image, size=(nh, nw), mode="bilinear", antialias=True, align_corners=False)
-        top, left = (nh - s) // 2, (nw - s) // 2
+        top, left = int(round((nh - s) / 2.0)), int(round((nw - s) / 2.0))   # torchvision's center_crop offsets
         image = image[..., top:top + s, left:left + s]
         mean = torch.tensor(self.mean, device=image.device, dtype=image.dtype)[None, :, None, None]
         std = torch.tensor(self.std, device=image.device, dtype=image.dtype)[None, :, None, None]

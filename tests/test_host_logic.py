@@ -95,3 +95,30 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_conditioner_mirror_against_reference_when_available():
+    """Row a2: DinoImageEncoder (conditioner.py:57-131) -- value-range shift, Resize(bilinear, antialias) + CenterCrop +
+    Normalize, HF Dinov2Model, cls token kept; zeros as the unconditional embedding.  Same small random model in both."""
+    ref_path = "/root/reference/Hunyuan3D-2/hy3dgen/shapegen/models/conditioner.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("/root/reference not present")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_conditioner", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
+    from r3g.conditioner import DinoImageEncoder, SingleImageEncoder
+    cfg = dict(hidden_size=32, num_hidden_layers=2, num_attention_heads=2, mlp_ratio=2, patch_size=14, image_size=56,
+               use_swiglu_ffn=True, layerscale_value=1.0, qkv_bias=True, hidden_act="gelu", layer_norm_eps=1e-6)
+    torch.manual_seed(0)
+    theirs = ref.DinoImageEncoder(config=cfg, use_cls_token=True, image_size=56)
+    mine = DinoImageEncoder(config=cfg, use_cls_token=True, image_size=56, device="cpu", dtype=torch.float32)
+    mine.model.load_state_dict(theirs.model.state_dict())
+    for shape in ((1, 3, 70, 90), (2, 3, 100, 64), (1, 3, 56, 56)):
+        img = torch.rand(shape) * 2 - 1
+        a, b = mine(img), theirs(img)
+        assert a.shape == b.shape == (shape[0], 17, 32)
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), (a - b).abs().max()
+    u = SingleImageEncoder(mine).unconditional_embedding(2)["main"]
+    assert u.shape == (2, 17, 32) and not u.any() and torch.equal(u, theirs.unconditional_embedding(2))
