@@ -20,7 +20,7 @@ from . import ops
 from .conditioner import DinoImageEncoder, SingleImageEncoder
 from .dit import Hunyuan3DDiT
 from .preprocessors import ImageProcessorV2
-from .scheduler import FlowMatchEulerDiscreteScheduler
+from .scheduler import FlowMatchEulerDiscreteScheduler, FlowMatchEulerDiscreteSchedulerOutput
 from .vae import ShapeVAE, SurfaceExtractors
 
 # Hunyuan3D-2 `hunyuan3d-dit-v2-0/config.yaml` values.  The checkpoint config is downloaded at run time by the
@@ -320,7 +320,9 @@ class Hunyuan3DDiTFlowMatchingPipeline(Hunyuan3DDiTPipeline):
                 ops.cfg_euler_step_(x, torch.cat([v, v]), 0.0, dsig[i], x_dup=None)
                 x_in.copy_(x)
             if callback is not None and i % callback_steps == 0:
-                callback(i, timesteps[i], x)
+                # pipelines.py:757-759: callback(step_idx, t, outputs) with outputs.prev_sample = the new latents
+                callback(i // getattr(self.scheduler, "order", 1), timesteps[i],
+                         FlowMatchEulerDiscreteSchedulerOutput(prev_sample=x))
         return x
 
     @torch.inference_mode()
