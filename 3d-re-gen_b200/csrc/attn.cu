@@ -1,16 +1,16 @@
 // r3g_attention: O = softmax(Q K^T * scale) V for head_dim 64, no mask -- flash-attention forward on tcgen05.
 //
 // One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so that one CTA's
-// softmax (MUFU-bound) overlaps the other's MMAs.
-//   warps 0..3  softmax / correction / epilogue: thread t owns query row t (TMEM lane t): row max and row
-//               sum need no shuffles; P is written as fp16 into a 128B-swizzled K-major smem tile
+// softmax (exp-unit bound at head_dim 64) overlaps the other's MMAs.
+//   warps 0..3  softmax / lazy correction / epilogue: thread t owns query row t (TMEM lane t): row max and row
+//               sum need no shuffles; P goes back to TMEM as packed fp16 and is the A operand of P V
 //   warp 4      TMA producer: Q once, then K and V tiles (128 x 64) through 2-deep rings
 //   warp 5      MMA issuer:  S = Q K^T  (M128 N128 K16 x4, accumulator in TMEM)
-//                            O_j = P V  (M128 N64  K16 x8, V consumed MN-major straight from its row-major tile)
-// O_j is accumulated in registers with the usual running-max rescale, so TMEM is never read-modify-written.
+//                            O += P V   (M128 N64  K16 x8, A from TMEM, V consumed MN-major from its row-major tile)
 // Call sites replaced: F.scaled_dot_product_attention in hunyuan3ddit.py:33-36 (L = 4442 joint txt+img tokens),
 // attention_blocks.py:328 (ShapeVAE, L = 3072), attention_processors.py:29-32 (geo-decoder cross attention,
-// Lk = 3072), vggt/layers/attention.py:61.
+// Lk = 3072), vggt/layers/attention.py:61.  Earlier kernel generations (registers-accumulated O, two threads per
+// row) live in the git history (round 1) with their measurements in profiles/README.md.
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -26,7 +26,6 @@ constexpr int kD = 64;
 constexpr int kBQ = 128;
 constexpr int kBKV = 128;
 constexpr int kKVStages = 2;
-constexpr int kThreads = 192;
 constexpr int kTileBytes = 128 * kD * 2;          // 16 KB: Q, K and V tiles
 constexpr int kPBytes = kBQ * kBKV * 2;           // 32 KB
 constexpr int kTilesBytes = kTileBytes * (1 + 2 * kKVStages) + kPBytes;  // 112 KB
@@ -47,226 +46,8 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-attention_kernel_v1(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
-  const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
-  uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
-  // barriers live in whichever end of the 1 KB slack is free
-  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
-  uint8_t* sV = sK + kKVStages * kTileBytes;
-  uint8_t* sP = sV + kKVStages * kTileBytes;
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
-  uint64_t* k_full = q_full + 1;
-  uint64_t* v_full = k_full + kKVStages;
-  uint64_t* k_empty = v_full + kKVStages;
-  uint64_t* v_empty = k_empty + kKVStages;
-  uint64_t* s_full = v_empty + kKVStages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBQ;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.Lk + kBKV - 1) / kBKV;
-
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kKVStages; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc<kTmemCols>(tmem_base_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % kKVStages;
-        const uint32_t ph = (j / kKVStages) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        tma_load_4d(sV + st * kTileBytes, &tmap_v, &v_full[st], 0, j * kBKV, h, b, kEvictLast);
-      }
-    }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
-    constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);  // B = V, MN-major
-    mbar_wait(q_full, 0);
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % kKVStages;
-      const uint32_t ph = (j / kKVStages) & 1;
-      mbar_wait(&k_full[st], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss(tmem_base + kTmemS, umma_desc_sw128(aq + k * 32, 1024, 16), umma_desc_sw128(ak + k * 32, 1024, 16),
-                  idesc_s, k ? 1u : 0u);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);
-      }
-      __syncwarp();
-      mbar_wait(p_full, j & 1);      // P_j is in smem; S and the previous O_j have been read out of TMEM
-      mbar_wait(&v_full[st], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k)
-          umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
-                  umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, k ? 1u : 0u);
-        umma_commit(o_full);
-        umma_commit(&v_empty[st]);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + output (warps 0..3)
-    const int row = threadIdx.x;             // 0..127 == TMEM lane
-    const uint32_t lane_base = (uint32_t)(warp * 32);
-    float acc[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t p_row = smem_u32(sP) + (row >> 3) * 1024 + (row & 7) * 128;
-    const int sw = row & 7;
-    for (int j = 0; j < n_kv; ++j) {
-      const int valid = min(kBKV, p.Lk - j * kBKV);  // columns of this tile that exist
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kBKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + c), v);
-        tmem_ld_wait();
-        if (c + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2(m_run - m_new);  // first tile: ex2(-inf) = 0
-      m_run = m_new;
-      // fold in the previous tile's P V, then rescale
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < kD; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c + i] = (acc[c + i] + __uint_as_float(v[i])) * alpha;
-        }
-      }
-      // pass 2: probabilities -> fp16 P tile in smem (the previous P V has completed: o_full was waited on)
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kBKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + c), v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-          float e1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
-          if (c + i >= valid) e0 = 0.f;
-          if (c + i + 1 >= valid) e1 = 0.f;
-          // the row sum uses the fp16-rounded probabilities that the P V product actually sees
-          __half2 hh = __floats2half2_rn(e0, e1);
-          float2 back = __half22float2(hh);
-          rs += back.x + back.y;
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        const uint32_t atom = p_row + (c >> 6) * (kBQ * 128);
-        const int u0 = (c & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t addr = atom + (((u0 + q) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                       : "memory");
-        }
-      }
-      l_run = l_run * alpha + rs;
-      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core's async proxy
-      tc_fence_before();          // orders this thread's TMEM loads before the MMA that overwrites S / O
-      mbar_arrive(p_full);
-    }
-    // last P V
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_run;
-    const int qrow = q0 + row;
-    __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl;
-#pragma unroll
-    for (int c = 0; c < kD; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + c), v);
-      tmem_ld_wait();
-      if (qrow < p.Lq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o4;
-          uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = c + 8 * q + 2 * i;
-            ow[i] = pack_half2((acc[e] + __uint_as_float(v[8 * q + 2 * i])) * inv_l,
-                               (acc[e + 1] + __uint_as_float(v[8 * q + 2 * i + 1])) * inv_l);
-          }
-          *reinterpret_cast<uint4*>(op + c + 8 * q) = o4;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// v2: software-pipelined.  Differences from v1 above:
+// Software pipeline:
 //   * the whole S row (128 fp32) is pulled into registers in one go, the TMEM S buffer is released at once
 //     (s_free) so the MMA warp issues S_{j+1} = Q K_{j+1}^T BEFORE P_j V_j: the tensor pipe works on the next
 //     scores while this tile's softmax runs;
@@ -629,341 +410,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// v3 = v2 with TWO threads per query row (8 softmax warps per CTA, 16 per SM): warp w and warp w+4 own the same 32
-// TMEM lanes and split the 128 score columns (and the 64 output columns) in halves.  Twice the warps per scheduler
-// hide the MUFU / TMEM latencies that left v2's exponent pipe half idle.  The two threads of a row exchange their
-// partial row maximum (every tile) and partial row sum (once, at the end) through spare TMEM columns -- there is no
-// shared memory left (2 CTAs x 113 KB) -- and meet on a 64-thread named barrier per warp pair.
-constexpr int kThreadsV3 = 320;           // warps 0..7 softmax, warp 8 TMA, warp 9 MMA
-
-constexpr uint32_t kTmemX = 192;          // exchange columns: [kTmemX + 2*parity + half]
-
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t v;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void pair_barrier(int quad) {
-  asm volatile("bar.sync %0, 64;\n" ::"r"(quad + 1) : "memory");
-}
-// publish `mine` to the partner thread of this row and fetch its value
-__device__ __forceinline__ float pair_exchange(uint32_t tmem_base, uint32_t lane_base, int quad, int half, int slot,
-                                               float mine) {
-  tmem_st1(tmem_addr(tmem_base, lane_base, kTmemX + 2 * slot + half), __float_as_uint(mine));
-  tmem_st_wait();
-  tc_fence_before();
-  pair_barrier(quad);
-  tc_fence_after();
-  const uint32_t other = tmem_ld1(tmem_addr(tmem_base, lane_base, kTmemX + 2 * slot + (half ^ 1)));
-  tmem_ld_wait();
-  return __uint_as_float(other);
-}
-// the same through shared memory (v4: the P tile lives in TMEM, so its 32 KB of shared memory are free)
-__device__ __forceinline__ float pair_exchange_smem(uint32_t xch, int quad, int half, int slot, int row, float mine) {
-  float other;
-  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(xch + (uint32_t)(((slot * 2 + half) * kBQ + row) * 4)), "f"(mine)
-               : "memory");
-  pair_barrier(quad);
-  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(other) : "r"(xch + (uint32_t)(((slot * 2 + (half ^ 1)) * kBQ + row) * 4))
-               : "memory");
-  return other;
-}
-
-// kPT (v4): the probabilities go to TMEM columns [kTmemP, kTmemP + 64) as packed halfs and P V is issued with the
-// A operand read from TMEM (tcgen05.mma [d], [a], b-desc).  That removes 64 KB of shared-memory traffic per tile
-// (32 KB of st.shared + 32 KB of operand fetch) from a kernel whose K/V/Q operand fetch and TMA fills already use
-// 80 KB per tile of the SM's 128 B/clk.
-constexpr uint32_t kTmemP = 192;
-// kF32: exponentials as scalar ex2.approx.f32 packed afterwards (2 FFMA + 2 MUFU + 1 F2FP per pair) instead of
-// ex2.approx.f16x2, which ptxas splits into 2 MUFU.EX2.F16 + a PRMT on top of the F2FP that feeds it.
-// kPoly: every kPoly-th pair of exponentials runs on the FMA pipe (0 = none).
-template <bool kPT, bool kF32, int kPoly, bool kF2 = false>
-__global__ void __launch_bounds__(kThreadsV3, 2)
-attention_kernel_v3(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uintptr_t raw = reinterpret_cast<uintptr_t>(smem_raw);
-  const uintptr_t aligned = (raw + 1023) & ~(uintptr_t)1023;
-  uint8_t* smem = reinterpret_cast<uint8_t*>(aligned);
-  uint8_t* bar_mem = (aligned - raw >= 128) ? smem_raw : smem + kTilesBytes;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
-  uint8_t* sV = sK + kKVStages * kTileBytes;
-  uint8_t* sP = sV + kKVStages * kTileBytes;
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(bar_mem);
-  uint64_t* k_full = q_full + 1;
-  uint64_t* v_full = k_full + kKVStages;
-  uint64_t* k_empty = v_full + kKVStages;
-  uint64_t* v_empty = k_empty + kKVStages;
-  uint64_t* s_full = v_empty + kKVStages;
-  uint64_t* s_free = s_full + 1;
-  uint64_t* p_full = s_free + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBQ;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.Lk + kBKV - 1) / kBKV;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kKVStages; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 9) tmem_alloc<kTmemCols>(tmem_base_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b, kEvictFirst);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % kKVStages;
-        const uint32_t ph = (j / kKVStages) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        tma_load_4d(sK + st * kTileBytes, &tmap_k, &k_full[st], 0, j * kBKV, h, b, kEvictLast);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        tma_load_4d(sV + st * kTileBytes, &tmap_v, &v_full[st], 0, j * kBKV, h, b, kEvictLast);
-      }
-    }
-  } else if (warp == 9) {
-    constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, false, false);
-    constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, kD, false, true);
-    const uint32_t aq = smem_u32(sQ);
-    auto issue_s = [&](int j) {
-      const int st = j % kKVStages;
-      mbar_wait(&k_full[st], (j / kKVStages) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t ak = smem_u32(sK + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss(tmem_base + kTmemS, umma_desc_sw128(aq + k * 32, 1024, 16), umma_desc_sw128(ak + k * 32, 1024, 16),
-                  idesc_s, k ? 1u : 0u);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) {
-        mbar_wait(s_free, j & 1);
-        issue_s(j + 1);
-      }
-      const int st = j % kKVStages;
-      mbar_wait(p_full, j & 1);
-      mbar_wait(&v_full[st], (j / kKVStages) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kBKV / 16; ++k) {
-          if (kPT)
-            umma_ts(tmem_base + kTmemO, tmem_base + kTmemP + k * 8, umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o,
-                    (j | k) ? 1u : 0u);
-          else
-            umma_ss(tmem_base + kTmemO, umma_desc_sw128(ap + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 1024, 16),
-                    umma_desc_sw128(av + k * 2048, 1024, 1024), idesc_o, (j | k) ? 1u : 0u);
-        }
-        umma_commit(o_full);
-        umma_commit(&v_empty[st]);
-      }
-      __syncwarp();
-    }
-  } else {
-    const uint32_t xch = smem_u32(sP);
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quad * 32);
-    constexpr int kHalf = kBKV / 2;                      // 64 score columns per thread
-    float m_used = -INFINITY, l_part = 0.f;
-    // this thread's P columns are exactly one 128-byte swizzle atom row
-    const uint32_t p_row = smem_u32(sP) + half * (kBQ * 128) + (row >> 3) * 1024 + (row & 7) * 128;
-    const int sw = row & 7;
-    for (int j = 0; j < n_kv; ++j) {
-      const int valid = min(kBKV, p.Lk - j * kBKV) - half * kHalf;   // valid columns among this thread's 64
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t s[kHalf];
-      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + half * kHalf), &s[0]);
-      tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemS + half * kHalf + 32), &s[32]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);
-      if (valid < kHalf) {
-#pragma unroll
-        for (int i = 0; i < kHalf; ++i)
-          if (i >= valid) s[i] = 0xff800000u;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < kHalf; i += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-      }
-      const float mine = fmaxf(mx0, mx1);
-      const float theirs = kPT ? pair_exchange_smem(xch, quad, half, j & 1, row, mine)
-                               : pair_exchange(tmem_base, lane_base, quad, half, j & 1, mine);
-      const float m_new = fmaxf(mine, theirs) * p.scale_log2;
-      bool waited_o = (j == 0);
-      if (j == 0) {
-        m_used = m_new;
-      } else {
-        const bool need = m_new - m_used > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {   // same rows, same m_new in both warps of the pair: same decision
-          mbar_wait(o_full, (j - 1) & 1);
-          tc_fence_after();
-          waited_o = true;
-          const float alpha = need ? ex2(m_used - m_new) : 1.f;
-#pragma unroll 1
-          for (int c = 0; c < kD / 2; c += 8) {
-            uint32_t o[8];
-            tmem_ld8(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2) + c), o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st8(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2) + c), o);
-          }
-          tmem_st_wait();
-          l_part *= alpha;
-          if (need) m_used = m_new;
-        }
-      }
-      float rs = 0.f;
-      uint32_t carry = 0;
-      const uint64_t scale2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(-m_used, -m_used);
-      uint32_t pk[kHalf / 2];
-#pragma unroll
-      for (int c = 0; c < kHalf; c += 16) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float x0, x1;
-          if (kF2) {
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 1])), scale2, nm2), x0, x1);
-          } else {
-            x0 = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_used);
-            x1 = fmaf(__uint_as_float(s[c + i + 1]), p.scale_log2, -m_used);
-          }
-          if (kPoly > 0 && (((c + i) >> 1) % (kPoly > 0 ? kPoly : 1)) == kPoly - 1) {
-            if (kF2) {
-              float e0, e1;
-              exp2_poly2(x0, x1, e0, e1);
-              pk[(c + i) >> 1] = cvt_f16x2(e0, e1);
-            } else {
-              pk[(c + i) >> 1] = cvt_f16x2(exp2_poly(x0), exp2_poly(x1));
-            }
-          } else if (kF32) {
-            pk[(c + i) >> 1] = cvt_f16x2(ex2(x0), ex2(x1));
-          } else {
-            pk[(c + i) >> 1] = ex2_f16x2(cvt_f16x2(x0, x1));
-          }
-        }
-        const uint32_t* q8 = &pk[c >> 1];
-        const uint32_t a01 = hadd2_u32(hadd2_u32(q8[0], q8[1]), hadd2_u32(q8[2], q8[3]));
-        const uint32_t a23 = hadd2_u32(hadd2_u32(q8[4], q8[5]), hadd2_u32(q8[6], q8[7]));
-        if (kF32) {
-          // 16 packed pairs (32 probabilities <= 1, partial sums <= 16) summed as half2 before the fp32 accumulate
-          const uint32_t a16 = hadd2_u32(a01, a23);
-          if ((c & 16) == 0) {
-            carry = a16;
-          } else {
-            const uint32_t a32 = hadd2_u32(carry, a16);
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a32));
-            rs += f.x + f.y;
-          }
-        } else {
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a01));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a23));
-          rs += (f0.x + f0.y) + (f1.x + f1.y);
-        }
-      }
-      l_part += rs;
-      if (!waited_o) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-      }
-      if (kPT) {
-        tmem_st32(tmem_addr(tmem_base, lane_base, kTmemP + half * (kHalf / 2)), pk);
-        tmem_st_wait();
-      } else {
-#pragma unroll
-        for (int c = 0; c < kHalf; c += 8) {
-          const uint32_t addr = p_row + ((((c >> 3)) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(pk[(c >> 1)]),
-                       "r"(pk[(c >> 1) + 1]), "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-      }
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float l_tot = l_part + (kPT ? pair_exchange_smem(xch, quad, half, n_kv & 1, row, l_part)
-                                      : pair_exchange(tmem_base, lane_base, quad, half, n_kv & 1, l_part));
-    const float inv_l = 1.f / l_tot;
-    const int qrow = q0 + row;
-    __half* op = p.o + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)qrow * p.o_sl + half * (kD / 2);
-    uint32_t v[32];
-    tmem_ld32(tmem_addr(tmem_base, lane_base, kTmemO + half * (kD / 2)), v);
-    tmem_ld_wait();
-    if (qrow < p.Lq) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o4;
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          ow[i] = pack_half2(__uint_as_float(v[8 * q + 2 * i]) * inv_l, __uint_as_float(v[8 * q + 2 * i + 1]) * inv_l);
-        *reinterpret_cast<uint4*>(op + 8 * q) = o4;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
 
 using AttnKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
-// Kernel generations kept for the parity tests and A/B runs (R3G_ATTN = family, R3G_ATTN_VARIANT = index):
-//   family 2 (one thread per row, the default): [0] as measured at r1c (P through shared memory, ex2.f16x2),
-//                                               [1] the default: P in TMEM, f32 exps, packed-fp32 softmax, 1/4 poly
-//   family 3 (two threads per row):             [0] as measured at r1d, [1] P in TMEM + f32 exps + 1/6 poly,
-//                                               [2] / [3] the same with the packed-fp32 softmax and 1/4 / 1/3 poly
-// The sweep over the other combinations (runs 16-23) is recorded in profiles/README.md.
-const AttnKernel kV3Variants[] = {attention_kernel_v3<false, false, 4>, attention_kernel_v3<true, true, 6>,
-                                  attention_kernel_v3<true, true, 4, true>, attention_kernel_v3<true, true, 3, true>};
-const AttnKernel kV2Variants[] = {attention_kernel<false, false, 0, 2>, attention_kernel<true, true, 4, 2, true>};
+// the shipped specialisation: P in TMEM, scalar f32 exponentials, every 4th pair polynomial, 2-deep K/V rings,
+// packed-fp32 softmax arithmetic (the sweep over the other combinations is recorded in profiles/README.md)
+const AttnKernel kAttention = attention_kernel<true, true, 4, 2, true>;
 
 int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int64_t sh, int64_t sl, int B, int H,
                  int L) {
@@ -976,6 +427,7 @@ int make_qkv_map(r3g_ctx* ctx, CUtensorMap* m, const void* base, int64_t sb, int
 }  // namespace
 
 extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* stream) {
+  r3g_device_guard guard(ctx);
   if (!ctx || !ctx->encode_tiled)
     return r3g_fail(ctx, R3G_E_CUDA, "attention: no CUDA device (there is no CPU fallback)");
   if (!a || !a->q || !a->k || !a->v || !a->o) return r3g_fail(ctx, R3G_E_INVALID, "attention: null argument");
@@ -992,38 +444,13 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
   p.o_sb = a->o_sb; p.o_sh = a->o_sh; p.o_sl = a->o_sl;
   p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  static bool use_v1 = false;
-  static int variant = 1, variant2 = 1;
-  static int version = 2;   // R3G_ATTN=1|2|3 selects the kernel generation (tests/test_gpu_linear_attention.py runs them)
-  if (!attr_set) {
-    const char* e = getenv("R3G_ATTN_V1");
-    use_v1 = e && e[0] == '1';
-    const char* ev = getenv("R3G_ATTN");
-    if (ev && ev[0] >= '1' && ev[0] <= '3') version = ev[0] - '0';
-    if (use_v1) version = 1;
-    for (AttnKernel fn : kV3Variants) {
-      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
-    const char* evar = getenv("R3G_ATTN_VARIANT");
-    if (evar && evar[0] >= '0' && evar[0] < '0' + (int)(sizeof(kV3Variants) / sizeof(kV3Variants[0]))) variant = evar[0] - '0';
-    if (evar && evar[0] >= '0' && evar[0] < '0' + (int)(sizeof(kV2Variants) / sizeof(kV2Variants[0]))) variant2 = evar[0] - '0';
-    for (AttnKernel fn : kV2Variants) {
-      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      R3G_CUDA_OK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+  if (!(ctx->attr_done & R3G_ATTR_ATTENTION)) {   // function attributes are per device: one flag per context
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(kAttention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(kAttention, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctx->attr_done |= R3G_ATTR_ATTENTION;
   }
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->H, a->B);
-  if (version == 1)
-    attention_kernel_v1<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
-  else if (version == 2)
-    kV2Variants[variant2]<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
-  else
-    kV3Variants[variant]<<<grid, kThreadsV3, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  kAttention<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -22,6 +22,13 @@ extern "C" int r3g_create(int device, r3g_ctx** out) {
     return R3G_E_CUDA;
   }
   *out = ctx;
+  ctx->gemm_2cta = -1;
+  // the caller's current device is left as it was (the entry points switch to ctx->device for their own duration)
+  struct Restore {
+    int prev = -1;
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
+  if (cudaGetDevice(&restore.prev) != cudaSuccess) restore.prev = -1;
   R3G_CUDA_OK(ctx, cudaSetDevice(device));
   cudaDeviceProp prop;
   R3G_CUDA_OK(ctx, cudaGetDeviceProperties(&prop, device));
@@ -42,6 +49,7 @@ extern "C" int r3g_create(int device, r3g_ctx** out) {
 
 extern "C" void r3g_destroy(r3g_ctx* ctx) {
   if (!ctx) return;
+  r3g_device_guard guard(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   free(ctx);
 }

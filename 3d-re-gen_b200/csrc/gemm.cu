@@ -517,11 +517,11 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
   p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = (a->N + BN - 1) / BN;
-  static bool attr_set = false;
-  if (!attr_set) {
+  constexpr unsigned kAttrBit = BN == 256 ? R3G_ATTR_LINEAR256 : BN == 128 ? R3G_ATTR_LINEAR128 : R3G_ATTR_LINEAR64;
+  if (!(ctx->attr_done & kAttrBit)) {
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::kSmemBytes));
-    attr_set = true;
+    ctx->attr_done |= kAttrBit;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
@@ -541,16 +541,9 @@ constexpr int kStageBytes2 = BM * BK * 2 + 128 * BK * 2;       // 16 KB of X + 1
 constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kNumEpilogueWarps * 768;
 constexpr int BN2 = 256;
 
-// kPairs = 2 (experiment, off by default -- see launch_linear_2cta): a cluster of FOUR CTAs = two CTA pairs working on
-// two M-adjacent 256 x 256 tiles that share the W tile.  Each CTA then fetches only a quarter of the W tile (64 rows)
-// per k-block and TMA-multicasts it to the CTA of the same rank in the other pair: 24 KB instead of 32 KB from L2 per
-// CTA and k-block.
-// A shared-memory slot is reusable when BOTH pairs' MMAs have read it (the other pair's CTA writes into it too), so
-// the empty barriers count one multicast commit per pair.
-template <int kPairs>
-__global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kNumThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                   const __grid_constant__ CUtensorMap tmap_w64, const LinearParams p) {
+                   const LinearParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
@@ -562,22 +555,18 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cluster_rank = cluster_ctarank();
-  const uint32_t cta_rank = cluster_rank & 1;            // rank inside the CTA pair
-  const int pair = (int)(cluster_rank >> 1);
+  const uint32_t cta_rank = cluster_ctarank();           // rank inside the CTA pair
   const bool leader = cta_rank == 0;
   const int num_k_blocks = (p.K + BK - 1) / BK;
-  // a cluster walks "super tiles" of kPairs M-adjacent 256-row tiles; pair `pair` owns tile row kPairs * sm + pair
-  const int num_tiles = ((p.tiles_m + kPairs - 1) / kPairs) * p.tiles_n;
-  const int cluster_id = blockIdx.x / (2 * kPairs), num_clusters = gridDim.x / (2 * kPairs);
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_w64);
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's expect_tx arrival; both CTAs' TMA bytes complete on it
-      mbar_init(&empty_bar[s], kPairs);   // one multicast tcgen05.commit per pair
+      mbar_init(&empty_bar[s], 1);   // the leader's multicast tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -597,7 +586,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int tm = min((tile / p.tiles_n) * kPairs + pair, p.tiles_m - 1), tn = tile % p.tiles_n;
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
         const int sg = tm / p.tiles_per_seg, l0 = (tm % p.tiles_per_seg) * 256 + (int)cta_rank * BM;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -607,11 +596,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           // complete before they land because the leader armed it with the bytes of BOTH CTAs)
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
           tma_load_3d_2sm(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
-          if (kPairs == 1)
-            tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
-          else   // my quarter of the W tile, to both CTAs of my rank
-            tma_load_2d_2sm_mc(sb + pair * (64 * BK * 2), &tmap_w64, &full_bar[stage], kb * BK,
-                               tn * BN2 + (int)cta_rank * 128 + pair * 64, (uint16_t)(0x5u << cta_rank), kEvictLast);
+          tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
       }
@@ -639,8 +624,8 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             for (int k = 0; k < BK / 16; ++k)
               umma_ss_2sm(d_tmem, umma_desc_sw128(sa + k * 32, 1024, 16), umma_desc_sw128(sb + k * 32, 1024, 16), idesc,
                           (kb | k) ? 1u : 0u);
-            umma_commit_2sm(&empty_bar[stage], kPairs == 1 ? 3 : 0xF);
-            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full_bar[acc], (uint16_t)(3u << (2 * pair)));
+            umma_commit_2sm(&empty_bar[stage], 3);
+            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full_bar[acc], 3);
           }
           __syncwarp();
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
@@ -655,13 +640,11 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint4* wsm = reinterpret_cast<uint4*>(epi_smem + (warp - 2) * kEpiSmemPerWarp);
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int tm_raw = (tile / p.tiles_n) * kPairs + pair, tn = tile % p.tiles_n;
-      const int tm = min(tm_raw, p.tiles_m - 1);
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int sg = tm / p.tiles_per_seg;
-      // a pair without a tile in the last super tile still runs the pipeline (it feeds the other pair's W quarter)
-      const int l = (tm_raw < p.tiles_m ? (tm % p.tiles_per_seg) * 256 : p.seg_len) + row_in_tile;
+      const int l = (tm % p.tiles_per_seg) * 256 + row_in_tile;
       const bool row_ok = l < p.seg_len;
       const int r = sg * p.seg_len + l;                          // logical row
       const int64_t out_row = (int64_t)sg * p.y_seg_stride + l;
@@ -707,7 +690,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 2 * pair);   // the pair leader's MMA warp owns the wait
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA warp owns the wait
     }
   }
 
@@ -756,60 +739,33 @@ int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
   p.tiles_m = nseg * p.tiles_per_seg;
   p.tiles_n = a->N / BN2;
-  CUtensorMap tw64;   // 64-row boxes of W: the quarter a CTA fetches and multicasts in the 4-CTA form
-  {
-    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    const uint64_t strides[2] = {2, (uint64_t)a->K * 2};
-    const uint32_t box[2] = {BK, 64};
-    int rc = r3g_make_tmap_f16(ctx, &tw64, a->w, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  static bool attr_set = false;
-  // R3G_GEMM_4CTA=1 selects the 4-CTA form.  Measured (run 29): only 33 four-CTA clusters are co-resident on the
-  // 148 SMs against 74 pairs, and the per-SM rate is unchanged (L2 already de-duplicates the pairs' W requests), so
-  // it loses 10 % (8884x7168x1024: 1044 vs 1157 TFLOP/s) and stays off.
-  static int quad_mode = 0;
-  if (!attr_set) {
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel_2cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel_2cta<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    const char* e = getenv("R3G_GEMM_4CTA");
-    if (e && e[0] == '1') quad_mode = 1;
-    attr_set = true;
+  if (!(ctx->attr_done & R3G_ATTR_LINEAR_2CTA)) {
+    R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    ctx->attr_done |= R3G_ATTR_LINEAR_2CTA;
   }
   // persistent grids are sized to the clusters that can be CO-RESIDENT (a GPC whose SM count is not a multiple of
   // the cluster size leaves SMs out; a cluster that has to wait for a slot would run as a second wave)
-  static int max_clusters2 = 0, max_clusters4 = 0;
-  if (!max_clusters2) {
-    auto query = [&](auto kern, int csize) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(ctx->num_sms / csize * csize));
-      cfg.blockDim = dim3(kNumThreads);
-      cfg.dynamicSmemBytes = kSmemBytes2;
-      cudaLaunchAttribute at;
-      at.id = cudaLaunchAttributeClusterDimension;
-      at.val.clusterDim.x = csize; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-      cfg.attrs = &at;
-      cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
-        (void)cudaGetLastError();
-        n = ctx->num_sms / csize;
-      }
-      return n < ctx->num_sms / csize ? n : ctx->num_sms / csize;
-    };
-    max_clusters2 = query(linear_kernel_2cta<1>, 2);
-    max_clusters4 = query(linear_kernel_2cta<2>, 4);
-    if (getenv("R3G_DEBUG_GEMM")) fprintf(stderr, "[r3g gemm] co-resident clusters: %d x2, %d x4\n", max_clusters2, max_clusters4);
+  if (!ctx->max_clusters2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->num_sms / 2 * 2));
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kSmemBytes2;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, linear_kernel_2cta, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = ctx->num_sms / 2;
+    }
+    ctx->max_clusters2 = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
+    if (getenv("R3G_DEBUG_GEMM")) fprintf(stderr, "[r3g gemm] co-resident CTA pairs: %d\n", ctx->max_clusters2);
   }
   const int tiles = p.tiles_m * p.tiles_n;
-  if (quad_mode && p.tiles_m >= 2) {
-    const int supers = ((p.tiles_m + 1) / 2) * p.tiles_n;
-    const int clusters = supers < max_clusters4 ? supers : max_clusters4;
-    linear_kernel_2cta<2><<<4 * clusters, kNumThreads, kSmemBytes2, s>>>(tx, tw, tw64, p);
-  } else {
-    const int clusters = tiles < max_clusters2 ? tiles : max_clusters2;
-    linear_kernel_2cta<1><<<2 * clusters, kNumThreads, kSmemBytes2, s>>>(tx, tw, tw64, p);
-  }
+  const int clusters = tiles < ctx->max_clusters2 ? tiles : ctx->max_clusters2;
+  linear_kernel_2cta<<<2 * clusters, kNumThreads, kSmemBytes2, s>>>(tx, tw, p);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -819,6 +775,7 @@ int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
 extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) {
   if (!ctx || !ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "linear: no CUDA device (there is no CPU fallback)");
   if (!a || !a->x || !a->w || !a->y) return r3g_fail(ctx, R3G_E_INVALID, "linear: null argument");
+  r3g_device_guard guard(ctx);
   if (a->M <= 0) return R3G_OK;
   if (a->N % 32 || a->K % 8 || a->ldx % 8 || a->ldy % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "linear: need N %% 32 == 0, K %% 8 == 0, ldx/ldy %% 8 == 0 (N=%d K=%d)", a->N,
@@ -854,8 +811,11 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
     const int64_t waves = (tiles + units - 1) / units;
     return factor * (double)tiles / (double)(waves * units);
   };
-  static int mode = -1;  // R3G_GEMM_2CTA=0 disables the CTA-pair kernel
-  if (mode < 0) { const char* e = getenv("R3G_GEMM_2CTA"); mode = (e && e[0] == '0') ? 0 : 1; }
+  if (ctx->gemm_2cta < 0) {   // R3G_GEMM_2CTA=0 disables the CTA-pair kernel
+    const char* e = getenv("R3G_GEMM_2CTA");
+    ctx->gemm_2cta = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int mode = ctx->gemm_2cta;
   const int64_t tm128 = (int64_t)nseg_ * ((seg_len_ + 127) / 128), tm256 = (int64_t)nseg_ * ((seg_len_ + 255) / 256);
   // measured: the CTA-pair tile wins for short K (epilogue-heavy), the single-CTA tile for K >= 4096
   const double e2 = (mode && a->N % 256 == 0) ? eff(tm256 * (a->N / 256), sms / 2, a->K <= 2048 ? 1.08 : 0.93) : 0.0;

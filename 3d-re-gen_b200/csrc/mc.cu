@@ -395,6 +395,7 @@ extern "C" int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int
                             size_t workspace_bytes, int64_t* nv_host, int64_t* nf_host, void* stream) {
   if (!ctx || !grid || !nv_host || !nf_host) return r3g_fail(ctx, R3G_E_INVALID, "mc_count: null argument");
   if (!ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "mc_count: no CUDA device (there is no CPU fallback)");
+  r3g_device_guard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   McDims d;
   McWorkspace w;
@@ -424,6 +425,8 @@ extern "C" int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, i
                               const double* bounds_host, void* workspace, size_t workspace_bytes, float* verts,
                               int32_t* faces, void* stream) {
   if (!ctx || !grid || !verts || !faces) return r3g_fail(ctx, R3G_E_INVALID, "mc_extract: null argument");
+  if (!ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "mc_extract: no CUDA device (there is no CPU fallback)");
+  r3g_device_guard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   McDims d;
   McWorkspace w;
@@ -449,6 +452,8 @@ extern "C" int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, i
 extern "C" int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level,
                                unsigned char* case_out, void* stream) {
   if (!ctx || !grid || !case_out) return r3g_fail(ctx, R3G_E_INVALID, "mc_classify: null argument");
+  if (!ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "mc_classify: no CUDA device (there is no CPU fallback)");
+  r3g_device_guard guard(ctx);
   McDims d;
   int rc = make_dims(ctx, n0, n1, n2, d);
   if (rc) return rc;

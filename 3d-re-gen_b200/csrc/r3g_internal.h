@@ -21,6 +21,28 @@ struct r3g_ctx {
   r3g_pfn_encode_tiled encode_tiled;
   // pinned host scratch for small device->host results (mc counts)
   int64_t* pinned;
+  // per-device lazy state (function attributes and occupancy queries are per device, a context is per device)
+  unsigned attr_done;          // R3G_ATTR_* bits: cudaFuncSetAttribute already applied on this context's device
+  int max_clusters2;           // co-resident CTA pairs of linear_kernel_2cta (0 = not queried yet)
+  int gemm_2cta;               // -1 = environment not read yet; R3G_GEMM_2CTA=0 disables the CTA-pair kernel
+};
+enum { R3G_ATTR_ATTENTION = 1, R3G_ATTR_LINEAR64 = 2, R3G_ATTR_LINEAR128 = 4, R3G_ATTR_LINEAR256 = 8,
+       R3G_ATTR_LINEAR_2CTA = 16, R3G_ATTR_MISC0 = 32, R3G_ATTR_MISC1 = 64, R3G_ATTR_MISC2 = 128 };
+
+// Every ABI entry point runs with the context's device current (a kernel cannot be launched into a stream of
+// another device) and restores the caller's device on return.
+struct r3g_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit r3g_device_guard(const r3g_ctx* ctx) {
+    if (ctx && ctx->encode_tiled && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+      switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~r3g_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  r3g_device_guard(const r3g_device_guard&) = delete;
+  r3g_device_guard& operator=(const r3g_device_guard&) = delete;
 };
 
 static inline int r3g_fail(r3g_ctx* ctx, int code, const char* fmt, ...) {

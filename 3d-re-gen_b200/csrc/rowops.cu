@@ -10,6 +10,9 @@
 using namespace r3g;
 
 namespace {
+// every fp16 row / vector these kernels touch moves as 16-byte accesses: pointers must be 16-byte aligned (leading
+// dimensions and column offsets are already required to be multiples of 8 halfs)
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -19,21 +22,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
 __device__ __forceinline__ float rnd_h(float x) { return __half2float(__float2half_rn(x)); }
 
+// Eight halfs moved as ONE 128-bit access.  The payload is a uint4 on purpose: with `__half2 v[4]` the struct copy is
+// member-wise and nvcc emits four 32-bit LDG/STG per Half8 even under alignas(16) (found in the SASS by
+// tests/test_sass.py), i.e. four quarter-used sector requests per lane instead of one coalesced 16-byte one.
 struct alignas(16) Half8 {
-  __half2 v[4];
+  uint4 u;
 };
-__device__ __forceinline__ void unpack8(const Half8& p, float* f) {
+__device__ __forceinline__ void unpack8(const Half8 p, float* f) {   // by value: the caller's load stays one 128-bit access
+  const __half2* v = reinterpret_cast<const __half2*>(&p.u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __half22float2(p.v[i]);
+    float2 t = __half22float2(v[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ Half8 pack8(const float* f) {
   Half8 p;
+  __half2* v = reinterpret_cast<__half2*>(&p.u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return p;
 }
 
@@ -546,7 +554,10 @@ __global__ void __launch_bounds__(256) points_fourier_kernel(const __half* __res
 __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi) {
   if (F == 8 && out_ld == 64 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
     // the geo-decoder's shape: the 51 features + 13 zeros of a row are built in registers and leave as eight
-    // 16-byte stores (a thread owns 128 contiguous bytes) instead of 64 strided 2-byte ones
+    // 16-byte stores (a thread owns 128 contiguous bytes) instead of 64 strided 2-byte ones.
+    // sinf / cosf (not the fast intrinsics) because torch.sin on an fp16 tensor is sinf of the widened value; their
+    // Payne-Hanek branch for |x| > 105615 is where this kernel's 32 bytes of stack come from -- unreachable for an
+    // fp16 argument (|e| <= 65504), so the local memory is never touched at run time.
     __half r[64];
 #pragma unroll
     for (int c = 0; c < 64; ++c) r[c] = __float2half_rn(0.f);
@@ -703,7 +714,8 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
 }  // namespace
 
 #define R3G_NEED_GPU(ctx, name) \
-  if (!(ctx) || !(ctx)->encode_tiled) return r3g_fail((ctx), R3G_E_CUDA, name ": no CUDA device (there is no CPU fallback)")
+  if (!(ctx) || !(ctx)->encode_tiled) return r3g_fail((ctx), R3G_E_CUDA, name ": no CUDA device (there is no CPU fallback)"); \
+  r3g_device_guard r3g_guard_(ctx)
 
 extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int width,
                              float eps, const void* w, const void* b, const void* scale, const void* shift,
@@ -714,6 +726,8 @@ extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, 
     return r3g_fail(ctx, R3G_E_INVALID, "layernorm: width %d must be a multiple of 8 and <= %d", width,
                     kLnMaxChunks * 256);
   if ((scale == nullptr) != (shift == nullptr)) return r3g_fail(ctx, R3G_E_INVALID, "layernorm: scale/shift pair");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(w) || !aligned16(b) || !aligned16(scale) || !aligned16(shift))
+    return r3g_fail(ctx, R3G_E_INVALID, "layernorm: pointers must be 16-byte aligned");
   if (rows <= 0) return R3G_OK;
   // persistent beyond one resident wave (3 blocks per SM at width <= 1024, 2 above)
   const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
@@ -736,6 +750,8 @@ extern "C" int r3g_layernorm_f32in(r3g_ctx* ctx, const float* x, int64_t ldx, vo
   if (width % 8 || width > kLnMaxChunks * 256 || ldx % 4 || ldy % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "layernorm_f32in: width %d must be a multiple of 8 and <= %d", width,
                     kLnMaxChunks * 256);
+  if (!aligned16(x) || !aligned16(y) || !aligned16(w) || !aligned16(b))
+    return r3g_fail(ctx, R3G_E_INVALID, "layernorm_f32in: pointers must be 16-byte aligned");
   if (rows <= 0) return R3G_OK;
   layernorm_f32in_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ldx, (__half*)y, ldy, rows, width, eps,
                                                                              (const __half*)w, (const __half*)b);
@@ -749,6 +765,8 @@ extern "C" int r3g_qk_norm_rope(r3g_ctx* ctx, void* qkv, int64_t ld, int64_t row
   R3G_NEED_GPU(ctx, "qk_norm_rope");
   if (ld % 8 || (q_w == nullptr) != (k_w == nullptr) || tokens_per_frame < 1 || patches_w < 1)
     return r3g_fail(ctx, R3G_E_INVALID, "qk_norm_rope: bad arguments");
+  if (!aligned16(qkv) || !aligned16(q_w) || !aligned16(q_b) || !aligned16(k_w) || !aligned16(k_b))
+    return r3g_fail(ctx, R3G_E_INVALID, "qk_norm_rope: pointers must be 16-byte aligned");
   const int64_t ngroups = rows * heads * 2;
   if (ngroups <= 0) return R3G_OK;
   qk_norm_rope_kernel<<<(unsigned)((ngroups * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -779,6 +797,8 @@ extern "C" int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int he
   R3G_NEED_GPU(ctx, "qk_norm");
   if (ld % 8 || q_off % 8 || k_off % 8 || head_stride % 8 || !q_w)
     return r3g_fail(ctx, R3G_E_INVALID, "qk_norm: offsets/strides must be multiples of 8 halfs");
+  if (!aligned16(buf) || !aligned16(q_w) || !aligned16(q_b) || !aligned16(k_w) || !aligned16(k_b))
+    return r3g_fail(ctx, R3G_E_INVALID, "qk_norm: pointers must be 16-byte aligned");
   const int nsel = k_w ? 2 : 1;
   const int64_t ngroups = (int64_t)rows * heads * nsel;
   if (ngroups <= 0) return R3G_OK;
@@ -795,6 +815,7 @@ extern "C" int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const voi
   R3G_NEED_GPU(ctx, "gemv");
   if (B < 1 || B > kGemvMaxB || K % 8 || vec_ld % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "gemv: B in [1,%d], K %% 8 == 0 required", kGemvMaxB);
+  if (!aligned16(w)) return r3g_fail(ctx, R3G_E_INVALID, "gemv: the weight matrix must be 16-byte aligned");
   const int bt = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : 8;
   const size_t smem = (size_t)bt * K * sizeof(float);
   if (smem > 48 * 1024) return r3g_fail(ctx, R3G_E_INVALID, "gemv: B_pad * K * 4 bytes must fit 48 KB of shared memory");
@@ -870,6 +891,7 @@ extern "C" int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows
                               void* stream) {
   R3G_NEED_GPU(ctx, "lnpost_dot");
   if (width % 8 || width > kLnMaxChunks * 256 || ldx % 8) return r3g_fail(ctx, R3G_E_INVALID, "lnpost_dot: width");
+  if (!aligned16(x)) return r3g_fail(ctx, R3G_E_INVALID, "lnpost_dot: x must be 16-byte aligned");
   if (rows <= 0) return R3G_OK;
   const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
   auto go = [&](auto kern) {

@@ -14,7 +14,7 @@ class DinoImageEncoder:
     mean = [0.485, 0.456, 0.406]
     std = [0.229, 0.224, 0.225]
 
-    def __init__(self, version=None, config=None, use_cls_token=True, image_size=518, device="cuda",
+    def __init__(self, version=None, config=None, use_cls_token=True, image_size=224, device="cuda",
                  dtype=torch.float16, **kwargs):
         from transformers import Dinov2Config, Dinov2Model
         if config is None and version is not None:

@@ -12,14 +12,22 @@ from . import _abi
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
 
+_call_device = None   # device of the op being issued (set by _ctx, read by _stream; contexts are not thread-safe)
+
+
 def _ctx(t):
+    """The r3g context of the tensor's device.  The library switches to that device for the duration of each call
+    (r3g_device_guard) and the launch goes to torch's current stream OF THAT DEVICE, so a pipeline on cuda:1 works
+    without torch.cuda.set_device(1)."""
+    global _call_device
     if not t.is_cuda:
         raise RuntimeError("r3g ops need CUDA tensors: there is no CPU fallback")
-    return _abi.get_context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    _call_device = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return _abi.get_context(_call_device)
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(_call_device).cuda_stream)
 
 
 def _p(t):

@@ -138,7 +138,7 @@ class Hunyuan3DDiTPipeline:
         cond = None
         if conditioner == "dinov2":
             torch.manual_seed(seed + 2)
-            cond = SingleImageEncoder(DinoImageEncoder(device=device, dtype=dtype))
+            cond = SingleImageEncoder(DinoImageEncoder(device=device, dtype=dtype, image_size=518))
         return cls(vae=vae, model=model, scheduler=sched, conditioner=cond,
                    image_processor=ImageProcessorV2(**cfg["image_processor"]), device=device, dtype=dtype, **kwargs)
 
@@ -167,11 +167,24 @@ class Hunyuan3DDiTPipeline:
         model.load_state_dict(ckpt["model"])
         vae = ShapeVAE(device=device, **config["vae"]["params"])
         vae.load_state_dict(ckpt["vae"])
-        enc_cfg = config["conditioner"]["params"]["main_image_encoder"]["params"]
-        enc = DinoImageEncoder(device=device, dtype=dtype, **enc_cfg)
+        # conditioner.py:239-246 + build_image_encoder: SingleImageEncoder(main_image_encoder={'type': ..., 'kwargs': ...})
+        cc = config["conditioner"]
+        if not str(cc.get("target", "")).endswith("SingleImageEncoder"):
+            raise NotImplementedError(f"conditioner target {cc.get('target')!r}: only SingleImageEncoder (the "
+                                      "Hunyuan3D-2 shape checkpoints' conditioner) is mirrored")
+        enc_cfg = cc["params"]["main_image_encoder"]
+        if enc_cfg.get("type") != "DinoImageEncoder":
+            raise NotImplementedError(f"main_image_encoder type {enc_cfg.get('type')!r}: only DinoImageEncoder is mirrored")
+        enc_kw = dict(enc_cfg.get("kwargs") or {})
+        enc_kw.setdefault("image_size", 224)          # ImageEncoder.__init__ default (conditioner.py:62)
+        enc = DinoImageEncoder(device=device, dtype=dtype, **enc_kw)
         if "conditioner" in ckpt:
-            sd = {k.replace("main_image_encoder.model.", ""): v for k, v in ckpt["conditioner"].items()}
-            enc.model.load_state_dict(sd, strict=False)
+            # conditioner.load_state_dict(ckpt['conditioner']) is strict in the reference (pipelines.py:179-180)
+            pre = "main_image_encoder.model."
+            bad = [k for k in ckpt["conditioner"] if not k.startswith(pre)]
+            if bad:
+                raise RuntimeError(f"unexpected conditioner keys (not under {pre!r}): {bad[:5]}")
+            enc.model.load_state_dict({k[len(pre):]: v for k, v in ckpt["conditioner"].items()}, strict=True)
         return cls(vae=vae, model=model, scheduler=FlowMatchEulerDiscreteScheduler(**config["scheduler"]["params"]),
                    conditioner=SingleImageEncoder(enc),
                    image_processor=ImageProcessorV2(**config["image_processor"]["params"]), device=device,
@@ -322,7 +335,7 @@ class Hunyuan3DDiTFlowMatchingPipeline(Hunyuan3DDiTPipeline):
             if callback is not None and i % callback_steps == 0:
                 # pipelines.py:757-759: callback(step_idx, t, outputs) with outputs.prev_sample = the new latents
                 callback(i // getattr(self.scheduler, "order", 1), timesteps[i],
-                         FlowMatchEulerDiscreteSchedulerOutput(prev_sample=x))
+                         FlowMatchEulerDiscreteSchedulerOutput(prev_sample=x.clone()))   # x is updated in place
         return x
 
     @torch.inference_mode()

@@ -53,7 +53,7 @@ def test_from_pretrained_maps_a_reference_layout_checkpoint(tmp_path, monkeypatc
            "vae": {"target": "hy3dgen.shapegen.models.ShapeVAE", "params": vae_p},
            "conditioner": {"target": "hy3dgen.shapegen.models.SingleImageEncoder",
                            "params": {"main_image_encoder": {"type": "DinoImageEncoder",
-                                                             "params": {"config": dino_p, "use_cls_token": True,
+                                                             "kwargs": {"config": dino_p, "use_cls_token": True,
                                                                         "image_size": 56}}}},
            "scheduler": {"target": "hy3dgen.shapegen.schedulers.FlowMatchEulerDiscreteScheduler",
                          "params": {"num_train_timesteps": 1000}},

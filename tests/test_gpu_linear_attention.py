@@ -145,27 +145,3 @@ def test_linear_fused_qk_norm(M, N, K, act, mode):
     d = (fused.float() - two_pass.float()).abs()
     assert d.max().item() <= 4e-3 and (d > 0).float().mean().item() < 0.02  # fp32 sum order only: rare 1-ulp flips
     assert (fused.float() - ref).abs().max().item() <= 6e-3
-
-
-@pytest.mark.parametrize("family,variant", [("1", "0"), ("2", "0"), ("3", "0"), ("3", "1")])
-def test_attention_kept_generations(family, variant):
-    """The earlier kernel generations stay selectable (R3G_ATTN / R3G_ATTN_VARIANT, read once per process): each is run in
-    its own interpreter against torch SDPA at a ragged shape (the default generation is what every other test uses)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, torch; sys.path.insert(0, %r)\n"
-        "from r3g import ops\n"
-        "torch.manual_seed(0)\n"
-        "q, k, v = (torch.randn(2, n, 4, 64, device='cuda').half() for n in (333, 777, 777))\n"
-        "o = ops.attention(q, k, v)\n"
-        "ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(),\n"
-        "                                                       v.transpose(1, 2).float()).transpose(1, 2)\n"
-        "err = (o.float() - ref).abs().max().item()\n"
-        "assert err <= 4e-3, err\n"
-        "print('ok', err)\n" % os.path.join(root, "3d-re-gen_b200"))
-    env = dict(os.environ, R3G_ATTN=family, R3G_ATTN_VARIANT=variant)
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=110)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]

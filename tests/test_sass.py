@@ -40,7 +40,7 @@ def _one(funcs, *needles):
 
 def test_gemm_is_tcgen05_tma_and_has_no_gpu_scope_membar(sass):
     funcs, usage = sass
-    for name in _one(funcs, "linear_kernel_2ctaILi1E") + _one(funcs, "linear_kernelILi256E"):
+    for name in _one(funcs, "linear_kernel_2cta") + _one(funcs, "linear_kernelILi256E"):
         body = funcs[name]
         assert "UTCHMMA" in body and "UTMALDG" in body and "LDTM" in body, name
         # the only GPU-scope membars allowed are the two cluster barriers (start / end of the kernel)
@@ -51,7 +51,7 @@ def test_gemm_is_tcgen05_tma_and_has_no_gpu_scope_membar(sass):
                     name + ": a GPU-scope membar outside the cluster barriers (a .release.cluster arrive in the pipeline?)"
         assert sum("MEMBAR.ALL.GPU" in ln for ln in ins) <= 2, name
         assert usage[name][1] <= 64, f"{name}: {usage[name][1]} bytes of stack (spills)"
-    assert "UTCHMMA.2CTA" in funcs[_one(funcs, "linear_kernel_2ctaILi1E")[0]]
+    assert "UTCHMMA.2CTA" in funcs[_one(funcs, "linear_kernel_2cta")[0]]
 
 
 def test_default_attention_uses_tmem_operand_mma_and_packed_fp32(sass):
@@ -72,10 +72,20 @@ def test_row_kernels_use_the_packed_fp32_pipe(sass):
     for needle in ("layernorm_kernelILi4E", "lnpost_dot_kernelILi4E"):
         body = funcs[_one(funcs, needle)[0]]
         assert "FFMA2" in body and "FADD2" in body, needle
-    # Known, not yet fixed on this branch: `struct alignas(16) Half8 { __half2 v[4]; }` is copied member-wise, so the
-    # row kernels issue four 32-bit LDG/STG per lane instead of one 128-bit access.  The fix (uint4 payload + alignment
-    # checks at the API, and this test asserting LDG.E.128 / STG.E.128) waits on branch `r2-half8` for a GPU run: it
-    # was found by reading this SASS after the round's GPU budget had been spent (profiles/README.md).
+    # every fp16 row moves as 16-byte accesses (a `__half2 v[4]` payload is copied member-wise: four 32-bit LDG/STG)
+    for needle in ("layernorm_kernelILi4E", "lnpost_dot_kernelILi4E", "qk_norm_kernel", "gemv_kernel"):
+        body = funcs[_one(funcs, needle)[0]]
+        assert "LDG.E.128" in body or "LDG.E.CONSTANT.128" in body or "LD.E.128" in body, needle
+    for needle in ("layernorm_kernelILi4E", "grid_fourier_kernel"):
+        assert "STG.E.128" in funcs[_one(funcs, needle)[0]], needle
+
+
+def test_no_spills_in_row_kernels(sass):
+    funcs, usage = sass
+    # (grid_fourier_kernel keeps 32 bytes of stack: sinf/cosf's Payne-Hanek branch, unreachable for fp16 arguments)
+    for needle in ("layernorm_kernelILi4E", "lnpost_dot_kernelILi4E", "qk_norm_kernel", "cfg_euler_kernel"):
+        name = _one(funcs, needle)[0]
+        assert usage[name][1] == 0, f"{name}: {usage[name][1]} bytes of stack"
 
 
 def test_marching_cubes_emit_has_no_output_atomics(sass):

@@ -16,8 +16,13 @@ algorithm (Lewiner et al. 2003, Chernyaev 1995, Nielson-Hamann 1991) is the stru
 
 The tables here are DERIVED from those rules: for every cubeindex and every outcome of the face
 tests on its ambiguous faces we trace the iso-contour segments on the six faces, chain them into
-closed loops and triangulate each loop.  Interior ("tunnel") tests of MC33 (sub-cases 4.2, 6.1.2,
-7.4.2, 10.1.2, 12.1.2, 13.5.2) are not generated -- see DESIGN.md "MC: what is and is not pinned".
+closed loops and triangulate each loop.  Where Lewiner's big switch applies `test_interior` (sub-cases 4.1,
+6.1, 7.4, 10.1, 12.1, 13.5) a second, "tunnel" tiling (4.1.2, 6.1.2, 7.4.2, 10.1.2, 12.1.2, 13.5.2: the two loops
+joined by a tube instead of capped separately) is generated together with the descriptor of the interior test
+(slice direction / reference edge and the sign whose connectivity is asked); the test itself (Lewiner's
+`test_interior`, restated from the published routine) runs in the oracle and in the kernel.  What is still NOT
+Lewiner's: the literal triangle order / diagonal choice of LookUpTable.h and the reference-edge column of his
+TEST6/7/12 and TILING13_5_1 tables (chosen here by a stated rule) -- see DESIGN.md section 4.
 
 Output: include/r3g_mc_tables.h (plain C arrays, included by the oracle and by the kernels).
 """
@@ -178,6 +183,178 @@ def triangulate(loops):
     return tris
 
 
+ANTIPODE = [CORNER.index(tuple(1 - c for c in p)) for p in CORNER]
+
+
+def surface_classes(ci, decisions):
+    """Union-find over the 8 corners: same-sign corners joined by a cube edge, or across an ambiguous face by
+    the face decision (pos_connected joins its two positive corners, otherwise its two negative ones)."""
+    par = list(range(8))
+
+    def find(a):
+        while par[a] != a:
+            par[a] = par[par[a]]
+            a = par[a]
+        return a
+
+    def join(a, b):
+        par[find(a)] = find(b)
+    sg = [(ci >> i) & 1 for i in range(8)]
+    for (a, b) in EDGE:
+        if sg[a] == sg[b]:
+            join(a, b)
+    for fi, pc in decisions.items():
+        f = FACE[fi]
+        want = 1 if pc else 0
+        pair = [c for c in f if sg[c] == want]
+        assert len(pair) == 2
+        join(pair[0], pair[1])
+    return [find(i) for i in range(8)], sg
+
+
+def loop_around(loops, ci, corners):
+    """The loop made exactly of the cube edges leaving the corner set `corners` (edges with one end inside)."""
+    want = sorted(ei for ei, (a, b) in enumerate(EDGE) if (a in corners) != (b in corners))
+    for i, lp in enumerate(loops):
+        if sorted(lp) == want:
+            return i
+    return None
+
+
+def interior_test(ci, decisions, loops):
+    """Where Lewiner's switch calls test_interior: returns (mode, ref_edge, sigma, loop_a, loop_b) or None.
+    mode 1 = the closed-form slice height along z (cases 4 and 10), mode 2 = slice through the iso-crossing of a
+    reference edge (cases 6, 7, 12, 13).  sigma = 1: the question is whether two POSITIVE corners are joined through
+    the interior, 0: two negative ones.  loop_a / loop_b: the loops the tunnel tiling joins."""
+    base = mc_case(ci)
+    if base not in (4, 6, 7, 10, 12, 13):
+        return None
+    cls, sg = surface_classes(ci, decisions)
+    if base == 13:
+        # 13.5: three faces around a corner N decide for N's opposite sign; N and its antipode are each cut off by
+        # a triangle, the rest is a hexagon (13.5.1).  The interior question is asked for the isolated corner of the
+        # configuration's own sign convention: positive for cubeindex 165 (corners 0,2,5,7), negative for its inverse.
+        if sum(1 for v in decisions.values() if v) != 3 or sorted(len(lp) for lp in loops) != [3, 3, 6]:
+            return None
+        sigma = 1 if ci == 165 else 0
+        iso = [c for c in range(8) if sg[c] == sigma and sum(1 for d in range(8) if cls[d] == cls[c]) == 1]
+        assert len(iso) == 1, (ci, decisions, iso)
+        P = iso[0]
+        la = loop_around(loops, ci, {P})
+        lb = [i for i, lp in enumerate(loops) if len(lp) == 6][0]
+        return (2, ref_edge_at(P, ci, None), sigma, la, lb)
+    cands = []
+    for P in range(8):
+        Q = ANTIPODE[P]
+        if P < Q and sg[P] == sg[Q] and cls[P] != cls[Q]:
+            cands.append((P, Q))
+    if base in (10, 12):
+        cands = [(P, Q) for (P, Q) in cands if sg[P] == 1]   # Lewiner tests the positive polarity only (TEST10/12 > 0)
+    if not cands:
+        return None
+    assert len(loops) == 2, (ci, decisions, loops)
+    sigma = sg[cands[0][0]]
+    assert all(sg[P] == sigma for P, _ in cands)
+    if base in (4, 10):
+        return (1, 15, sigma, 0, 1)
+    # reference edge: at the corner of the pair that is alone in its class (all three cube edges there cross)
+    P, Q = cands[0]
+    size = lambda c: sum(1 for d in range(8) if cls[d] == cls[c])  # noqa: E731
+    if size(P) != 1:
+        P, Q = Q, P
+    assert size(P) == 1, (ci, decisions)
+    amb_with_P = [fi for fi in decisions if P in FACE[fi] and Q not in FACE[fi]]
+    face = None
+    if base in (6, 12):
+        # the face whose test sent us here contains P and a corner of Q's class on its diagonal
+        face = [fi for fi in decisions if P in FACE[fi]]
+        assert len(face) >= 1
+        face = face[0] if base == 6 else face
+    return (2, ref_edge_at(P, ci, face), sigma, 0, 1)
+
+
+def ref_edge_at(P, ci, faces):
+    """Reference edge of the slice test: a crossing cube edge at corner P; among those lying on the tested
+    ambiguous face(s) (if given) the one along the highest axis (z > y > x).  This reproduces the two rows of
+    Lewiner's TEST6 that could be recalled ({2,7,10} for corners 0,1,6 and {4,7,11} for 0,1,7); the full column is
+    not reconstructible without the table."""
+    if faces is not None and not isinstance(faces, (list, tuple)):
+        faces = [faces]
+    best = None
+    for ei, (a, b) in enumerate(EDGE):
+        if P not in (a, b):
+            continue
+        if ((ci >> a) & 1) == ((ci >> b) & 1):
+            continue
+        if faces is not None and not any(a in FACE[f] and b in FACE[f] for f in faces):
+            continue
+        axis = [i for i in range(3) if CORNER[a][i] != CORNER[b][i]][0]
+        if best is None or axis > best[0]:
+            best = (axis, ei)
+    assert best is not None, (P, ci, faces)
+    return best[1]
+
+
+def _mid(e):
+    if e == 12:
+        return (0.5, 0.5, 0.5)
+    return tuple((CORNER[EDGE[e][0]][i] + CORNER[EDGE[e][1]][i]) / 2 for i in range(3))
+
+
+def tunnel(loop_a, loop_b):
+    """Triangulate the tube between two loops (the 4.1.2 / 6.1.2 / 7.4.2 / 10.1.2 / 12.1.2 / 13.5.2 tilings): a strip
+    of len(a) + len(b) triangles that walks loop_a forwards and loop_b backwards.  Both loops are given in the STORED
+    winding (see triangulate), which is the boundary orientation the tube needs: a strip triangle covers the boundary
+    edge a_i -> a_{i+1} (or b_{j-1} -> b_j) in that direction.  Preference: fewest rungs lying in a cube face (7.4.2
+    has no strip without one: each vertex of the triangle sees only two hexagon vertices off its faces), then least
+    total rung length between edge midpoints; ties by enumeration order, so the table is deterministic."""
+    A, B = loop_a, loop_b
+    m, n = len(A), len(B)
+
+    def cone_free(steps):
+        # n retreats (or m advances) in a row, cyclically, would fan a whole loop around one vertex: a closed cone
+        N = len(steps)
+        for want, lim in ((True, m), (False, n)):
+            run = best_run = 0
+            for k in range(2 * N):
+                run = run + 1 if steps[k % N] == want else 0
+                best_run = max(best_run, run)
+            if best_run >= lim:
+                return False
+        return True
+
+    def d(u, v):
+        return sum((a - b) ** 2 for a, b in zip(_mid(u), _mid(v))) ** 0.5
+    best = None
+    for j0 in range(n):
+        # state (i, j): current rung A[i] -- B[j]; advance A: tri (A[i], A[i+1], B[j]); retreat B: tri (B[j-1], B[j], A[i])
+        for mask in itertools.combinations(range(m + n), m):
+            steps = [k in mask for k in range(m + n)]
+            if not cone_free(steps):
+                continue
+            i, j, tris, cost, in_face = 0, j0, [], 0.0, 0
+            for adv in steps:
+                u, v = A[i % m], B[j % n]
+                in_face += 1 if edges_share_face(u, v) else 0
+                cost += d(u, v)
+                if adv:
+                    tris.append((u, A[(i + 1) % m], v))
+                    i += 1
+                else:
+                    tris.append((B[(j - 1) % n], v, u))
+                    j -= 1
+            key = (in_face, round(cost, 9))
+            if best is None or key < best[0]:
+                best = (key, tris)
+    assert best is not None, "no tunnel strip"
+    return best[1]
+
+
+def stored(lp):
+    """Traced loop -> stored winding (see the comment in triangulate)."""
+    return [lp[0]] + lp[:0:-1]
+
+
 def mc_case(ci):
     """Lorensen/Chernyaev/Lewiner base-case number 0..14 of a cube index (shape invariant)."""
     def shape(bits):
@@ -230,6 +407,9 @@ def main(out_path):
     tri = []
     ntil = 0
     case = [mc_case(ci) for ci in range(256)]
+    interior = []      # per tiling: 0 = no interior test, else mode | ref_edge << 2 | sigma << 6
+    tunnel_of = []     # per tiling: index of the tunnel tiling chosen when the interior test says "connected"
+    pending = []       # (tiling index, loops, la, lb) whose tunnel tilings are appended after the face-test tilings
     for ci in range(256):
         amb = ambiguous_faces(ci)
         m = 0
@@ -239,11 +419,32 @@ def main(out_path):
         offset[ci] = ntil
         for sub_id in range(1 << len(amb)):
             dec = {f: bool((sub_id >> j) & 1) for j, f in enumerate(amb)}
-            t = triangulate(loops_for(ci, dec))
+            loops = loops_for(ci, dec)
+            t = triangulate(loops)
             for (a, b, c) in t:
                 tri.extend((a, b, c))
             tiling_start.append(len(tri))
+            it = interior_test(ci, dec, loops)
+            if it is None:
+                interior.append(0)
+            else:
+                mode, edge, sigma, la, lb = it
+                interior.append(mode | (edge << 2) | (sigma << 6))
+                pending.append((ntil, loops, la, lb))
+            tunnel_of.append(0xFFFF)
             ntil += 1
+    n_face_tilings = ntil
+    for (til, loops, la, lb) in pending:
+        t = tunnel(stored(loops[la]), stored(loops[lb]))
+        rest = [lp for i, lp in enumerate(loops) if i not in (la, lb)]
+        t = t + triangulate(rest)
+        for (a, b, c) in t:
+            tri.extend((a, b, c))
+        tiling_start.append(len(tri))
+        tunnel_of[til] = ntil
+        interior.append(0)
+        tunnel_of.append(0xFFFF)
+        ntil += 1
     # --- self checks -------------------------------------------------------------------------
     # (1) single positive corner v0: in the core (x,y,z) frame the normal points AWAY from v0.
     t0 = tri[tiling_start[offset[1]]:tiling_start[offset[1] + 1]]
@@ -266,12 +467,17 @@ def main(out_path):
     with open(out_path, "w") as f:
         w = f.write
         w("/* GENERATED by tools/gen_mc_tables.py -- do not edit.\n")
-        w(" * Marching-cubes tables restated from the published Lewiner/Chernyaev rules (face tests only);\n")
+        w(" * Marching-cubes tables restated from the published Lewiner/Chernyaev rules (face tests + interior tests);\n")
         w(" * replaces scikit-image's _marching_cubes_lewiner_luts (third-party, not in the reference tree),\n")
         w(" * call site Hunyuan3D-2/hy3dgen/shapegen/models/autoencoders/surface_extractors.py:69-73. */\n")
         w("#ifndef R3G_MC_TABLES_H\n#define R3G_MC_TABLES_H\n")
         w("#ifndef R3G_MC_TABLE_QUAL\n#define R3G_MC_TABLE_QUAL static const\n#endif\n")
-        w(f"#define R3G_MC_NUM_TILINGS {ntil}\n#define R3G_MC_TRI_ENTRIES {len(tri)}\n#define R3G_MC_MAX_TRIS {max_tris}\n")
+        w(f"#define R3G_MC_NUM_TILINGS {ntil}\n#define R3G_MC_NUM_FACE_TILINGS {n_face_tilings}\n")
+        w(f"#define R3G_MC_TRI_ENTRIES {len(tri)}\n#define R3G_MC_MAX_TRIS {max_tris}\n")
+        w("/* scikit-image's `FLT_EPSILON = np.spacing(1.0)` (_marching_cubes_lewiner_cy.pyx; SURVEY.md Appendix A.5): the\n")
+        w(" * one tiny constant of the vertex weights 1/(eps+|v|), of test_face and of test_internal -- 2^-52, not the\n")
+        w(" * float32 epsilon of Lewiner's C++ (1.19e-7).  Shared by the oracle and the kernels. */\n")
+        w("#define R3G_MC_EPS 2.220446049250313e-16\n")
 
         def arr(ctype, name, data, per=16):
             w(f"R3G_MC_TABLE_QUAL {ctype} {name}[{len(data)}] = {{\n")
@@ -283,6 +489,12 @@ def main(out_path):
         arr("unsigned short", "r3g_mc_tiling_offset", offset)
         arr("unsigned short", "r3g_mc_tiling_start", tiling_start)
         arr("unsigned char", "r3g_mc_tri", tri, per=24)
+        # interior test per tiling (0 = none): bits 0..1 mode (1 = closed-form slice along z: cases 4 / 10,
+        # 2 = slice through the crossing of a reference edge: cases 6 / 7 / 12 / 13), bits 2..5 reference edge,
+        # bit 6 sigma (1: are two POSITIVE corners joined through the interior, 0: two negative ones);
+        # r3g_mc_tunnel[t] = tiling used instead of t when the answer is "joined" (0xFFFF = none)
+        arr("unsigned char", "r3g_mc_interior", interior)
+        arr("unsigned short", "r3g_mc_tunnel", tunnel_of)
         # geometry helpers
         arr("unsigned char", "r3g_mc_edge_corner", [c for e in EDGE for c in e], per=2)
         arr("unsigned char", "r3g_mc_corner_xyz", [c for p in CORNER for c in p], per=3)
@@ -295,8 +507,25 @@ def main(out_path):
             axis = [i for i in range(3) if pa[i] != pb[i]][0]
             info.append(lo[0] | (lo[1] << 1) | (lo[2] << 2) | (axis << 3))
         arr("unsigned char", "r3g_mc_edge_info", info, per=12)
+        # slice of the interior test through the iso-crossing of reference edge e = (u, w) (Lewiner test_interior,
+        # `case 6/7/12/13`): the three parallel cube edges (b0,b1), (c0,c1), (d0,d1) in the direction u -> w, with
+        # (c0,c1) the one diagonal to e in the slice: At = 0, Bt = v[b0] + (v[b1]-v[b0]) t, ...; t = v[u] / (v[u] - v[w])
+        sl = []
+        for (u, wv) in EDGE:
+            pu, pw = CORNER[u], CORNER[wv]
+            axis = [i for i in range(3) if pu[i] != pw[i]][0]
+            lo, hi = [i for i in range(3) if i != axis]
+
+            def flip(p, axes):
+                q = list(p)
+                for a_ in axes:
+                    q[a_] = 1 - q[a_]
+                return CORNER.index(tuple(q))
+            for axes in ((lo,), (lo, hi), (hi,)):
+                sl.extend((flip(pu, axes), flip(pw, axes)))
+        arr("unsigned char", "r3g_mc_slice", sl, per=6)
         w("#endif\n")
-    print(f"tilings={ntil} tri_entries={len(tri)} max_tris={max_tris}", file=sys.stderr)
+    print(f"tilings={ntil} (tunnel {ntil - n_face_tilings}) tri_entries={len(tri)} max_tris={max_tris}", file=sys.stderr)
 
 
 if __name__ == "__main__":
