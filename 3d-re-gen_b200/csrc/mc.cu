@@ -39,7 +39,50 @@ __device__ __forceinline__ bool face_pos_connected(const double* cv, int face) {
   // explicit roundings: no fma contraction, so the decision does not depend on the compiler's contraction choices
   double ac = __dmul_rn(A, C), bd = __dmul_rn(B, D);
   double pmn = (A > 0.0) ? __dsub_rn(ac, bd) : __dsub_rn(bd, ac);
-  return pmn > -(double)FLT_EPSILON;
+  return pmn > -R3G_MC_EPS;
+}
+
+// Lewiner's test_interior (scikit-image: test_internal) for the sub-cases 4, 6.1, 7.4, 10.1, 12.1, 13.5: is the pair of
+// same-sign corners on a body diagonal joined through the interior of the cell (then the tunnel tiling is used)?
+// desc = r3g_mc_interior entry (mode, reference edge, sigma), see tools/gen_mc_tables.py.  Every product / sum is an
+// explicitly rounded operation in source order (no fma contraction): the decision does not depend on the compiler.
+__device__ __forceinline__ double lerp_rn(double a, double b, double t) {
+  return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), t));
+}
+__device__ __noinline__ bool interior_joined(const double* cv, int desc) {
+  const int mode = desc & 3, edge = (desc >> 2) & 15, sigma = (desc >> 6) & 1;
+  double At, Bt, Ct, Dt;
+  if (mode == 1) {
+    const double d40 = __dsub_rn(cv[4], cv[0]), d62 = __dsub_rn(cv[6], cv[2]);
+    const double d73 = __dsub_rn(cv[7], cv[3]), d51 = __dsub_rn(cv[5], cv[1]);
+    const double a = __dsub_rn(__dmul_rn(d40, d62), __dmul_rn(d73, d51));
+    const double b = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(cv[2], d40), __dmul_rn(cv[0], d62)), __dmul_rn(cv[1], d73)),
+                               __dmul_rn(cv[3], d51));
+    const double t = __ddiv_rn(-b, __dmul_rn(2.0, a));
+    if (t < 0.0 || t > 1.0) return sigma == 0;
+    At = lerp_rn(cv[0], cv[4], t);
+    Bt = lerp_rn(cv[3], cv[7], t);
+    Ct = lerp_rn(cv[2], cv[6], t);
+    Dt = lerp_rn(cv[1], cv[5], t);
+  } else {
+    const int u = r3g_mc_edge_corner[2 * edge], w = r3g_mc_edge_corner[2 * edge + 1];
+    const unsigned char* sl = &r3g_mc_slice[6 * edge];
+    const double t = __ddiv_rn(cv[u], __dsub_rn(cv[u], cv[w]));
+    At = 0.0;
+    Bt = lerp_rn(cv[sl[0]], cv[sl[1]], t);
+    Ct = lerp_rn(cv[sl[2]], cv[sl[3]], t);
+    Dt = lerp_rn(cv[sl[4]], cv[sl[5]], t);
+  }
+  const int test = (At >= 0.0 ? 1 : 0) + (Bt >= 0.0 ? 2 : 0) + (Ct >= 0.0 ? 4 : 0) + (Dt >= 0.0 ? 8 : 0);
+  const double acbd = __dsub_rn(__dmul_rn(At, Ct), __dmul_rn(Bt, Dt));
+  bool pos_joined;
+  switch (test) {
+    case 7: case 11: case 13: case 14: case 15: pos_joined = true; break;
+    case 5: pos_joined = !(acbd < R3G_MC_EPS); break;
+    case 10: pos_joined = !(acbd >= R3G_MC_EPS); break;
+    default: pos_joined = false; break;
+  }
+  return sigma ? pos_joined : !pos_joined;
 }
 
 // Does cell (x,y,z) create the vertex on its edge e?  (first cell in traversal order sharing the edge)
@@ -86,6 +129,8 @@ __device__ __forceinline__ Cell eval_cell(const float* raw, float level, double*
       ++j;
     }
   c.til = r3g_mc_tiling_offset[c.ci] + sub;
+  const int idesc = r3g_mc_interior[c.til];
+  if (idesc && interior_joined(cv, idesc)) c.til = r3g_mc_tunnel[c.til];
   int t0 = r3g_mc_tiling_start[c.til], t1 = r3g_mc_tiling_start[c.til + 1];
   c.nt = (t1 - t0) / 3;
   unsigned seen = 0;
@@ -281,14 +326,14 @@ __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __rest
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const unsigned char* o = &r3g_mc_corner_xyz[3 * i];
-        double w = 1.0 / ((double)FLT_EPSILON + fabs(cv[i]));
+        double w = 1.0 / (R3G_MC_EPS + fabs(cv[i]));
         fx += o[0] * w; fy += o[1] * w; fz += o[2] * w; ff += w;
       }
     } else {
       const int a = r3g_mc_edge_corner[2 * e], b = r3g_mc_edge_corner[2 * e + 1];
       const unsigned char *oa = &r3g_mc_corner_xyz[3 * a], *ob = &r3g_mc_corner_xyz[3 * b];
-      double wa = 1.0 / ((double)FLT_EPSILON + fabs(cv[a]));
-      double wb = 1.0 / ((double)FLT_EPSILON + fabs(cv[b]));
+      double wa = 1.0 / (R3G_MC_EPS + fabs(cv[a]));
+      double wb = 1.0 / (R3G_MC_EPS + fabs(cv[b]));
       fx = oa[0] * wa + ob[0] * wb;   // offsets are 0/1: products exact, fma-safe
       fy = oa[1] * wa + ob[1] * wb;
       fz = oa[2] * wa + ob[2] * wb;

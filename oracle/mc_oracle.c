@@ -9,13 +9,16 @@
  *
  * PARITY UNPINNED against scikit-image: the algorithm lives in scikit-image (>=0.24, requirements.txt:17),
  * which is neither vendored in /root/reference nor installed here, and the reference holds no golden
- * meshes.  This file follows the published algorithm and scikit-image's documented conventions
- * (SURVEY.md Appendix A): sequential traversal `for z: for y: for x` over cells with x = last array
- * axis; cubeindex bit i set iff (v_i - level) > 0 in Lewiner's corner order; one vertex per
- * sign-changing grid edge created on first use and shared; vertex position by the
- * inverse-|value|-weighted centre of mass in double, stored float32; output vertices in array-axis
- * order; faces in the default gradient_direction='descent' winding.  The tiling tables are the
- * generated include/r3g_mc_tables.h (tools/gen_mc_tables.py), not Lewiner's LookUpTable.h.
+ * meshes (tests/test_mc_skimage_golden.py compares against tests/golden/skimage_mc_*.npz as soon as a machine
+ * with scikit-image has run tools/dump_skimage_goldens.py).  This file follows the published algorithm and
+ * scikit-image's conventions: sequential traversal `for z: for y: for x` over cells with
+ * x = last array axis; cubeindex bit i set iff (v_i - level) > 0 in Lewiner's corner order; Lewiner's test_face
+ * on every ambiguous face and test_interior where his switch applies it (4, 6.1, 7.4, 10.1, 12.1, 13.5);
+ * one vertex per sign-changing grid edge created on first use and shared; vertex position by the
+ * inverse-(eps+|value|)-weighted centre of mass in double with eps = np.spacing(1.0), stored float32; output
+ * vertices in array-axis order; faces in the default gradient_direction='descent' winding.  The tiling tables are
+ * the generated include/r3g_mc_tables.h (tools/gen_mc_tables.py), not Lewiner's LookUpTable.h: which sub-case a
+ * cell falls into follows Lewiner's tests, the triangle order / diagonals inside a cell are our own.
  *
  * The implementation is deliberately the simple sequential one (hash-free "first user creates the
  * vertex" with per-edge id arrays), independent in structure from the scan-based CUDA kernels. */
@@ -58,13 +61,56 @@ static void push_face(mesh_t *m, int a, int b, int c) {
 /* Face test (Lewiner test_face, restated symmetrically): on an ambiguous face with diagonal
  * products P (the two positive corners) and N (the two negative corners), the positive corners
  * are joined through the face iff the bilinear saddle value is >= 0  <=>  P - N >= 0; ties within
- * FLT_EPSILON count as joined.  Doubles, like the reference's Cython core. */
+ * R3G_MC_EPS count as joined (`if fabs(AC_BD) < FLT_EPSILON: return face >= 0`).  Doubles, like the Cython core. */
 static int face_pos_connected(const double *cv, int face) {
   const unsigned char *fc = &r3g_mc_face_corner[4 * face];
   double A = cv[fc[0]], B = cv[fc[1]], C = cv[fc[2]], D = cv[fc[3]];
   double ac = A * C, bd = B * D;
   double pmn = (A > 0.0) ? (ac - bd) : (bd - ac);
-  return pmn > -(double)FLT_EPSILON;
+  return pmn > -R3G_MC_EPS;
+}
+
+/* Lewiner's test_interior (MarchingCubes.cpp; scikit-image: test_internal), restated.  desc = r3g_mc_interior entry:
+ * mode 1 (cases 4, 10): the slice z = t where At*Ct - Bt*Dt is extremal, A on v0->v4, B on v3->v7, C on v2->v6,
+ * D on v1->v5; t outside [0,1] answers `s > 0`.  mode 2 (cases 6, 7, 12, 13): the slice through the iso-crossing of
+ * the reference edge, At = 0.  The positive corners of the slice square are joined iff >= 3 of them are positive, or
+ * the diagonal pair is positive and the bilinear saddle has their sign.  sigma = 1 (s > 0): the tunnel tiling is
+ * taken iff the positive corners are joined; sigma = 0 (s < 0): iff they are not.  Returns 1 for the tunnel tiling. */
+static int interior_joined(const double *cv, int desc) {
+  const int mode = desc & 3, edge = (desc >> 2) & 15, sigma = (desc >> 6) & 1;
+  double At, Bt, Ct, Dt;
+  if (mode == 1) {
+    const double a = (cv[4] - cv[0]) * (cv[6] - cv[2]) - (cv[7] - cv[3]) * (cv[5] - cv[1]);
+    const double b = cv[2] * (cv[4] - cv[0]) + cv[0] * (cv[6] - cv[2]) - cv[1] * (cv[7] - cv[3]) -
+                     cv[3] * (cv[5] - cv[1]);
+    const double t = -b / (2.0 * a);
+    if (t < 0.0 || t > 1.0) return sigma == 0;   /* `return s > 0`: "separate" for s > 0, the tunnel for s < 0 */
+    At = cv[0] + (cv[4] - cv[0]) * t;
+    Bt = cv[3] + (cv[7] - cv[3]) * t;
+    Ct = cv[2] + (cv[6] - cv[2]) * t;
+    Dt = cv[1] + (cv[5] - cv[1]) * t;
+  } else {
+    const int u = r3g_mc_edge_corner[2 * edge], w = r3g_mc_edge_corner[2 * edge + 1];
+    const unsigned char *sl = &r3g_mc_slice[6 * edge];
+    const double t = cv[u] / (cv[u] - cv[w]);
+    At = 0.0;
+    Bt = cv[sl[0]] + (cv[sl[1]] - cv[sl[0]]) * t;
+    Ct = cv[sl[2]] + (cv[sl[3]] - cv[sl[2]]) * t;
+    Dt = cv[sl[4]] + (cv[sl[5]] - cv[sl[4]]) * t;
+  }
+  int test = 0;
+  if (At >= 0.0) test += 1;
+  if (Bt >= 0.0) test += 2;
+  if (Ct >= 0.0) test += 4;
+  if (Dt >= 0.0) test += 8;
+  int pos_joined;
+  switch (test) {
+    case 7: case 11: case 13: case 14: case 15: pos_joined = 1; break;
+    case 5: pos_joined = !(At * Ct - Bt * Dt < R3G_MC_EPS); break;
+    case 10: pos_joined = !(At * Ct - Bt * Dt >= R3G_MC_EPS); break;
+    default: pos_joined = 0; break;
+  }
+  return sigma ? pos_joined : !pos_joined;
 }
 
 /* Returns 0 on success, 1 if level is outside [min,max] (skimage ValueError), 2 if no surface
@@ -116,6 +162,7 @@ int r3g_oracle_marching_cubes(const float *vol, int n0, int n1, int n2, float le
             ++j;
           }
         int til = r3g_mc_tiling_offset[ci] + sub;
+        if (r3g_mc_interior[til] && interior_joined(cv, r3g_mc_interior[til])) til = r3g_mc_tunnel[til];
         int t0 = r3g_mc_tiling_start[til], t1 = r3g_mc_tiling_start[til + 1];
         int ids[3];
         for (int t = t0; t < t1; ++t) {
@@ -138,14 +185,14 @@ int r3g_oracle_marching_cubes(const float *vol, int n0, int n1, int n2, float le
             if (e == 12) {
               for (int i = 0; i < 8; ++i) {
                 const unsigned char *o = &r3g_mc_corner_xyz[3 * i];
-                double w = 1.0 / ((double)FLT_EPSILON + fabs(cv[i]));
+                double w = 1.0 / (R3G_MC_EPS + fabs(cv[i]));
                 fx += o[0] * w; fy += o[1] * w; fz += o[2] * w; ff += w;
               }
             } else {
               int a = r3g_mc_edge_corner[2 * e], b = r3g_mc_edge_corner[2 * e + 1];
               const unsigned char *oa = &r3g_mc_corner_xyz[3 * a], *ob = &r3g_mc_corner_xyz[3 * b];
-              double wa = 1.0 / ((double)FLT_EPSILON + fabs(cv[a]));
-              double wb = 1.0 / ((double)FLT_EPSILON + fabs(cv[b]));
+              double wa = 1.0 / (R3G_MC_EPS + fabs(cv[a]));
+              double wb = 1.0 / (R3G_MC_EPS + fabs(cv[b]));
               fx = oa[0] * wa + ob[0] * wb;
               fy = oa[1] * wa + ob[1] * wb;
               fz = oa[2] * wa + ob[2] * wb;

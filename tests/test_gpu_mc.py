@@ -18,6 +18,16 @@ def _vols():
     yield "noise_ragged", rng.normal(size=(7, 12, 9)).astype(np.float32)
     yield "noise20", rng.normal(size=(20, 20, 20)).astype(np.float32)
     yield "tiny2", np.array([[[1, -1], [-1, -1]], [[-1, -1], [-1, 1]]], np.float32)
+    # one isolated cell per cube index x 6 log-normal magnitude draws: every face-test sub-case, and Lewiner's interior
+    # test on both sides for 4.1.1 / 4.1.2 and 10.1.1 / 10.1.2 (tools/dump_skimage_goldens.py: case_atlas)
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "dump_goldens", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "dump_skimage_goldens.py"))
+    dg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dg)
+    yield "case_atlas", dg.case_atlas(0)
+    yield "noise_closed", dg.white_noise((17, 18, 19), 3)
 
 
 @pytest.mark.parametrize("name,vol", list(_vols()))

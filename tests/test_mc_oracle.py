@@ -1,6 +1,11 @@
-"""CPU: the marching-cubes oracle against topological / geometric invariants (config 1 of BASELINE.json:
-64^3 synthetic sphere SDF -> marching cubes on CPU).  scikit-image is not available, so the oracle is
-"parity unpinned" against it; these properties are what any correct Lewiner-style extraction satisfies."""
+"""CPU: the marching-cubes oracle (oracle/mc_oracle.c, table driven) against
+  * topological / geometric invariants (config 1 of BASELINE.json: 64^3 synthetic sphere SDF -> marching cubes on CPU),
+  * a SECOND, independent implementation (oracle/mc_tracer.py: every cell traced from the rules, no generated tables,
+    no ownership predicate) -- bit for bit, order included,
+  * an independent numpy check of the topology on every grid face (iso-segments predicted from the four corner signs
+    and Lewiner's face test).
+scikit-image is not available, so the oracle stays "parity unpinned" against it (tests/test_mc_skimage_golden.py
+activates when goldens exist); these properties are what any correct Lewiner-style extraction satisfies."""
 import numpy as np
 import pytest
 
@@ -106,7 +111,7 @@ def test_vertices_on_sign_changing_edges_and_formula():
         a, b = float(vol[tuple(lo)]) - float(lvl), float(vol[tuple(hi)]) - float(lvl)
         if (p - np.floor(p) > 0).any():
             assert (a > 0) != (b > 0)
-            eps = float(np.finfo(np.float32).eps)
+            eps = float(np.spacing(1.0))      # scikit-image's FLT_EPSILON (include/r3g_mc_tables.h: R3G_MC_EPS)
             wa, wb = 1 / (eps + abs(a)), 1 / (eps + abs(b))
             expect = np.float32(lo[axis] + wb / (wa + wb))
             assert p[axis] == expect
@@ -137,3 +142,115 @@ def test_ragged_shapes():
     v, f = omc.marching_cubes(vol, 0.0)
     assert check_closed_manifold(v, f) == 2
     assert v[:, 0].max() <= 6 and v[:, 1].max() <= 11 and v[:, 2].max() <= 8
+
+
+def noise(shape, seed):
+    vol = np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+    vol[0, :, :] = vol[-1, :, :] = vol[:, 0, :] = vol[:, -1, :] = vol[:, :, 0] = vol[:, :, -1] = -1.0   # closed surface
+    return vol
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (12, 13, 14)), (1, (14, 12, 13)), (2, (9, 9, 9))])
+def test_table_oracle_equals_independent_tracer_on_white_noise(seed, shape):
+    """White noise holds every base case and every face-test sub-case, and the interior test fires both ways
+    (4.1.1 / 4.1.2, 10.1.1 / 10.1.2)."""
+    import mc_tracer
+    vol = noise(shape, seed)
+    v, f, cases = omc.marching_cubes(vol, 0.0, return_cases=True)
+    tv, tf, sub = mc_tracer.marching_cubes(vol, 0.0, return_subcases=True)
+    assert np.array_equal(v, tv) and np.array_equal(f, tf)
+    assert check_closed_manifold(v, f) % 2 == 0
+    if seed == 0:
+        assert set(np.unique(cases)) == set(range(15))
+        kinds = {(k[0], k[2]) for k in sub}
+        assert (4, "tunnel") in kinds and (4, "tested-separate") in kinds
+        assert {(b, "tested-separate") for b in (6, 7, 10, 12)} <= kinds
+
+
+def test_tracer_equals_oracle_on_smooth_fields_and_level_shift():
+    import mc_tracer
+    for vol, lvl in ((random_field(15, 3), 0.1), (torus(17), 0.0), (sphere(13), -0.05)):
+        v, f = omc.marching_cubes(vol, lvl)
+        tv, tf = mc_tracer.marching_cubes(vol, lvl)
+        assert np.array_equal(v, tv) and np.array_equal(f, tf)
+
+
+def test_tunnel_cells_of_case_10():
+    """Two strong opposite edges joined through a weak interior: Lewiner's test_interior picks 10.1.2."""
+    import mc_tracer
+    found = 0
+    rng = np.random.default_rng(7)
+    for _ in range(4000):
+        c = rng.standard_normal(8) * np.exp(1.5 * rng.standard_normal(8))
+        c = np.abs(c) * np.array([1, 1, -1, -1, -1, -1, 1, 1])      # corners 0,1 and 6,7 positive: base case 10
+        vol = np.full((4, 4, 4), -5.0, np.float32)
+        for i, (x, y, z) in enumerate([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]):
+            vol[1 + z, 1 + y, 1 + x] = c[i]
+        tv, tf, sub = mc_tracer.marching_cubes(vol, 0.0, return_subcases=True)
+        if any(k[0] == 10 and k[2] == "tunnel" for k in sub):
+            found += 1
+            v, f = omc.marching_cubes(vol, 0.0)
+            assert np.array_equal(v, tv) and np.array_equal(f, tf)
+            assert check_closed_manifold(v, f) == 2          # ONE component of genus 0 through the tunnel
+    assert found >= 5
+
+
+def test_face_topology_against_an_independent_numpy_prediction():
+    """On every grid face (the square between two cells) the mesh must carry exactly the iso-segments that the four
+    corner signs and Lewiner's face test predict: computed here with numpy from the volume alone, no tables."""
+    vol = noise((11, 12, 10), 5)
+    v, f = omc.marching_cubes(vol, 0.0)
+    eps = float(np.spacing(1.0))
+    # key of a vertex: the grid edge it sits on = (axis, lower grid point); centre vertices have three fractional parts
+    frac = v - np.floor(v)
+    nfrac = (frac > 0).sum(1)
+    lo = np.floor(v).astype(int)
+    axis = np.argmax(frac > 0, axis=1)
+    key = {}
+    for i in range(len(v)):
+        if nfrac[i] <= 1:
+            key[i] = (int(axis[i]) if nfrac[i] == 1 else -1, tuple(lo[i]))
+    und = set()
+    for a, b, c in f:
+        for p, q in ((a, b), (b, c), (c, a)):
+            und.add((min(p, q), max(p, q)))
+    by_edge = {}
+    for i, k in key.items():
+        by_edge.setdefault(k, i)
+    n = vol.shape
+    checked = extra = 0
+    for normal in range(3):
+        u_ax, w_ax = [a for a in range(3) if a != normal]
+        for p0 in np.ndindex(*[n[a] - (0 if a == normal else 1) for a in range(3)]):
+            p = np.array(p0)
+            if p[normal] in (0, n[normal] - 1):
+                continue                                # faces on the volume boundary have a cell on one side only
+            def val(du, dw):
+                q = p.copy(); q[u_ax] += du; q[w_ax] += dw
+                return float(vol[tuple(q)])
+            c00, c10, c11, c01 = val(0, 0), val(1, 0), val(1, 1), val(0, 1)       # cyclic A, B, C, D
+            s = [c > 0 for c in (c00, c10, c11, c01)]
+            if sum(s) in (0, 4):
+                continue
+            def edge_vertex(k):                          # vertex on side k of the square (A-B, B-C, C-D, D-A)
+                q = p.copy()
+                if k == 0: ax = u_ax
+                elif k == 1: q[u_ax] += 1; ax = w_ax
+                elif k == 2: q[w_ax] += 1; ax = u_ax
+                else: ax = w_ax
+                return by_edge[(ax, tuple(q))]
+            crossing = [k for k in range(4) if s[k] != s[(k + 1) % 4]]
+            if len(crossing) == 2:
+                expect = {tuple(sorted((edge_vertex(crossing[0]), edge_vertex(crossing[1]))))}
+            else:
+                acbd = c00 * c11 - c10 * c01
+                pos_joined = True if abs(acbd) < eps else ((acbd >= 0) == (c00 > 0))
+                # corners cut off: the negative ones if the positive pair is joined, else the positive ones
+                cut = [k for k in range(4) if s[k] != pos_joined]
+                expect = {tuple(sorted((edge_vertex((k - 1) % 4), edge_vertex(k)))) for k in cut}
+            on_face = {edge_vertex(k) for k in crossing}
+            have = {e for e in und if e[0] in on_face and e[1] in on_face}
+            assert expect <= have, (p0, normal)
+            extra += len(have - expect)                  # rungs of tunnel tilings may lie in a face (7.4.2 only)
+            checked += 1
+    assert checked > 500 and extra == 0

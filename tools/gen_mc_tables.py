@@ -463,6 +463,20 @@ def main(out_path):
                 key = (v[i], v[(i + 1) % 3])
                 assert key not in half, "duplicate directed edge in tiling"
                 half[key] = 1
+    # (3) a tunnel tiling replaces its face-test tiling inside the same cell: same boundary (the directed edges used
+    #     once), so the neighbouring cells see no difference
+    def boundary(til):
+        tt = tri[tiling_start[til]:tiling_start[til + 1]]
+        d = set()
+        for k in range(0, len(tt), 3):
+            v = tt[k:k + 3]
+            for i in range(3):
+                d.add((v[i], v[(i + 1) % 3]))
+        return {e for e in d if (e[1], e[0]) not in d}
+    for til in range(n_face_tilings):
+        if tunnel_of[til] != 0xFFFF:
+            assert interior[til] != 0
+            assert boundary(til) == boundary(tunnel_of[til]), "tunnel tiling changes the cell boundary"
     max_tris = max(tiling_start[i + 1] - tiling_start[i] for i in range(ntil)) // 3
     with open(out_path, "w") as f:
         w = f.write
