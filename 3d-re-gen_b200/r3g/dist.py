@@ -75,3 +75,169 @@ def gather_meshes(meshes, to_host=False, max_objects=None):
             for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, payload, 0)]):
                 w.wait()
     return out
+
+
+class MeshStreamGatherer:
+    """Per-object gather to rank 0, overlapped with the next object's compute ("run it on a side
+    stream so rank 0 can start writing .glbs while others finish").
+
+    Every rank calls `submit(verts, faces)` once per step (None, None when it has no object in that step) right after
+    its object has been enqueued; all ranks make the same number of calls.  A step is one fixed-capacity message per
+    peer -- [nv, nf, verts..., faces...] as int32 words -- so rank 0 can post its receives without knowing the sizes
+    and without a host round trip; the messages move over NCCL on a SIDE stream (NVLink / NVSwitch; a few hundred MB
+    per step) while the compute stream runs the next object.  On rank 0 the sizes are read one step later (by then the
+    step's header copy has long landed: no stall), the payloads go device -> PINNED ring -> a consumer thread that
+    hands the arrays to `sink(step, rank, verts, faces)` (default: keep them for `finish()`).  Nothing on this path is
+    a pageable synchronous `.cpu()` (round 1's limiter: 4.8 GB/s into rank 0).
+
+    Also runs on gloo with CPU tensors (tests/test_dist_gloo.py), where streams do not exist and every wait is a host
+    wait."""
+
+    def __init__(self, cap_vertices, cap_faces, device=None, to_host=True, depth=2, sink=None):
+        import queue
+        import threading
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda") and (
+            not dist.is_initialized() or dist.get_backend() == "nccl")
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu"))
+        self.cap_v, self.cap_f = int(cap_vertices), int(cap_faces)
+        self.cap = 4 + 3 * self.cap_v + 3 * self.cap_f
+        self.depth, self.to_host, self.step = depth, to_host, 0
+        self.side = torch.cuda.Stream(self.device) if self.cuda else None
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.send = [torch.empty(self.cap, **i32) for _ in range(depth)]
+        self.results, self.sink = {}, sink
+        self.pending = []            # rank 0: steps whose headers have been requested but whose payloads are not read yet
+        if self.rank == 0:
+            self.recv = [[torch.empty(self.cap, **i32) for _ in range(self.world - 1)] for _ in range(depth)]
+            pin = self.cuda
+            self.hdr = [torch.empty(self.world, 4, dtype=torch.int32, pin_memory=pin) for _ in range(depth)]
+            self.land = [[torch.empty(self.cap, dtype=torch.int32, pin_memory=pin) for _ in range(self.world)]
+                         for _ in range(depth)] if to_host else None
+            self.slot_free = [threading.Event() for _ in range(depth)]
+            for e in self.slot_free:
+                e.set()
+            self.q = queue.Queue()
+            self.err = None
+            self.thread = threading.Thread(target=self._consume, daemon=True)
+            self.thread.start()
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _stream(self):
+        import contextlib
+        return torch.cuda.stream(self.side) if self.cuda else contextlib.nullcontext()
+
+    def _pack(self, buf, verts, faces):
+        nv = 0 if verts is None else int(verts.shape[0])
+        nf = 0 if faces is None else int(faces.shape[0])
+        if nv > self.cap_v or nf > self.cap_f:
+            raise ValueError(f"mesh ({nv} vertices, {nf} faces) exceeds the gather capacity ({self.cap_v}, {self.cap_f})")
+        buf[:4] = torch.tensor([nv, nf, 0, 0], dtype=torch.int32).to(buf.device, non_blocking=True)
+        if nv:
+            buf[4:4 + 3 * nv].copy_(verts.reshape(-1).contiguous().view(torch.int32), non_blocking=True)
+        if nf:
+            buf[4 + 3 * nv:4 + 3 * nv + 3 * nf].copy_(faces.reshape(-1).to(torch.int32), non_blocking=True)
+        return nv, nf
+
+    def _consume(self):
+        try:
+            while True:
+                item = self.q.get()
+                if item is None:
+                    return
+                step, slot, event, sizes = item
+                if event is not None:
+                    event.synchronize()
+                for r, (nv, nf) in enumerate(sizes):
+                    src = self.land[slot][r] if self.to_host else (self.send[slot] if r == 0 else self.recv[slot][r - 1])
+                    v = src[4:4 + 3 * nv].view(torch.float32).view(nv, 3).clone()
+                    f = src[4 + 3 * nv:4 + 3 * nv + 3 * nf].view(nf, 3).clone()
+                    if nv == 0 and nf == 0:
+                        continue
+                    if self.sink is not None:
+                        self.sink(step, r, v, f)
+                    else:
+                        self.results[(step, r)] = (v, f)
+                self.slot_free[slot].set()
+        except Exception as e:      # surfaced by finish()
+            self.err = e
+            for ev in self.slot_free:
+                ev.set()
+
+    def _read_payloads(self, step, slot, hdr_event):
+        """rank 0, one step later: sizes are on the host now; copy exactly the used words into the pinned ring."""
+        if hdr_event is not None:
+            hdr_event.synchronize()
+        sizes = [(int(self.hdr[slot][r, 0]), int(self.hdr[slot][r, 1])) for r in range(self.world)]
+        event = None
+        if self.to_host and self.cuda:
+            with self._stream():
+                for r, (nv, nf) in enumerate(sizes):
+                    n = 4 + 3 * nv + 3 * nf
+                    src = self.send[slot] if r == 0 else self.recv[slot][r - 1]
+                    self.land[slot][r][:n].copy_(src[:n], non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(self.side)
+        elif self.to_host:
+            for r, (nv, nf) in enumerate(sizes):
+                n = 4 + 3 * nv + 3 * nf
+                self.land[slot][r][:n].copy_((self.send[slot] if r == 0 else self.recv[slot][r - 1])[:n])
+        self.q.put((step, slot, event, sizes))
+
+    # ------------------------------------------------------------------------------------------------ API
+    def submit(self, verts, faces):
+        step, slot = self.step, self.step % self.depth
+        self.step += 1
+        if self.rank == 0:
+            # the previous step's sizes are on the host by now (its messages left the peers a whole object ago):
+            # queue its payload copies BEFORE this step's receives, so a late peer cannot hold them up
+            while self.pending:
+                self._read_payloads(*self.pending.pop(0))
+            # the slot's previous occupant (step - depth) must have left the pinned ring
+            self.slot_free[slot].wait()
+            self.slot_free[slot].clear()
+        if self.cuda:
+            self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with self._stream():
+            self._pack(self.send[slot], verts, faces)
+            if self.world > 1:
+                if self.rank == 0:
+                    works = dist.batch_isend_irecv([dist.P2POp(dist.irecv, self.recv[slot][r - 1], r)
+                                                    for r in range(1, self.world)])
+                else:
+                    works = dist.batch_isend_irecv([dist.P2POp(dist.isend, self.send[slot], 0)])
+                for w in works:
+                    w.wait()          # NCCL: orders the side stream after the transfer; gloo: host wait
+            if self.rank == 0:
+                self.hdr[slot][0].copy_(self.send[slot][:4], non_blocking=True)
+                for r in range(1, self.world):
+                    self.hdr[slot][r].copy_(self.recv[slot][r - 1][:4], non_blocking=True)
+                ev = None
+                if self.cuda:
+                    ev = torch.cuda.Event()
+                    ev.record(self.side)
+                self.pending.append((step, slot, ev))     # its payloads are read at the next submit() / finish()
+        if self.cuda:
+            # a send buffer may be repacked only after its transfer: the NEXT use of this slot is ordered on the side
+            # stream; the caller's tensors (verts / faces) must outlive the copy: tie them to the side stream
+            for t in (verts, faces):
+                if t is not None and t.is_cuda:
+                    t.record_stream(self.side)
+
+    def finish(self):
+        """Drain.  Returns, on rank 0, [(verts, faces)] ordered by (rank, step) -- gather_meshes' order; [] elsewhere."""
+        if self.rank != 0:
+            if self.cuda:
+                self.side.synchronize()
+            return []
+        while self.pending:
+            self._read_payloads(*self.pending.pop(0))
+        self.q.put(None)
+        self.thread.join()
+        if self.err is not None:
+            raise self.err
+        if self.cuda:
+            self.side.synchronize()
+        return [self.results[k] for k in sorted(self.results, key=lambda k: (k[1], k[0]))]

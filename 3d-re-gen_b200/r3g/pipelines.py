@@ -354,6 +354,8 @@ class Hunyuan3DDiTFlowMatchingPipeline(Hunyuan3DDiTPipeline):
         if cond is None:
             cond_inputs = self.prepare_image(image)
             image_t = cond_inputs.pop("image")
+            if self.device.type == "cuda":       # the crop crosses PCIe once, from pinned memory, asynchronously
+                image_t = image_t.pin_memory().to(self.device, non_blocking=True)
             cond = self.encode_cond(image_t, cond_inputs, do_cfg)
             batch_size = image_t.shape[0]
         else:

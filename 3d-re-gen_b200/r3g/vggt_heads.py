@@ -204,3 +204,75 @@ class VGGT:
 
     def to(self, *a, **k):
         return self
+
+
+def random_state_dict(seed=0, embed_dim=1024, depth=24, vit_depth=24, trunk_depth=4, features=256,
+                      out_channels=(256, 512, 1024, 1024), patch_size=14, img_size=518, std=0.02):
+    """Seeded random weights with the key names and shapes of VGGT-1B's camera + depth model (SURVEY.md Appendix C;
+    vggt/models/vggt.py, aggregator.py:71-120, camera_head.py:28-70, dpt_head.py:53-113).  No checkpoint is reachable
+    from this build environment, so bench.py's config-4 workload and the GPU tests run on these."""
+    g = torch.Generator().manual_seed(seed)
+    C = embed_dim
+    sd = {}
+
+    def rn(*shape, s=std):
+        return torch.randn(*shape, generator=g) * s
+
+    def block(p, dim, qk_norm):
+        for n, shp in (("attn.qkv", (3 * dim, dim)), ("attn.proj", (dim, dim)), ("mlp.fc1", (4 * dim, dim)),
+                       ("mlp.fc2", (dim, 4 * dim))):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = rn(*shp), rn(shp[0])
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = 1 + rn(dim, s=0.05), rn(dim)
+        if qk_norm:
+            for n in ("attn.q_norm", "attn.k_norm"):
+                sd[p + n + ".weight"], sd[p + n + ".bias"] = 1 + rn(64, s=0.05), rn(64)
+        sd[p + "ls1.gamma"], sd[p + "ls2.gamma"] = torch.full((dim,), 0.1), torch.full((dim,), 0.1)
+
+    a = "aggregator."
+    sd[a + "camera_token"], sd[a + "register_token"] = rn(1, 2, 1, C), rn(1, 2, 4, C)
+    pe = a + "patch_embed."
+    sd[pe + "patch_embed.proj.weight"], sd[pe + "patch_embed.proj.bias"] = rn(C, 3, patch_size, patch_size), torch.zeros(C)
+    sd[pe + "cls_token"], sd[pe + "register_tokens"] = rn(1, 1, C), rn(1, 4, C)
+    sd[pe + "pos_embed"] = rn(1, 1 + (img_size // patch_size) ** 2, C)
+    sd[pe + "mask_token"] = torch.zeros(1, C)
+    sd[pe + "norm.weight"], sd[pe + "norm.bias"] = torch.ones(C), torch.zeros(C)
+    for i in range(vit_depth):
+        block(f"{pe}blocks.{i}.", C, False)
+    for i in range(depth):
+        block(f"{a}frame_blocks.{i}.", C, True)
+        block(f"{a}global_blocks.{i}.", C, True)
+    D = 2 * C
+    c = "camera_head."
+    for n in ("token_norm", "trunk_norm"):
+        sd[c + n + ".weight"], sd[c + n + ".bias"] = torch.ones(D), torch.zeros(D)
+    sd[c + "empty_pose_tokens"] = torch.zeros(1, 1, 9)
+    for n, shp in (("embed_pose", (D, 9)), ("poseLN_modulation.1", (3 * D, D)), ("pose_branch.fc1", (D // 2, D)),
+                   ("pose_branch.fc2", (9, D // 2))):
+        sd[c + n + ".weight"], sd[c + n + ".bias"] = rn(*shp), rn(shp[0])
+    for i in range(trunk_depth):
+        block(f"{c}trunk.{i}.", D, False)
+        sd[f"{c}trunk.{i}.ls1.gamma"], sd[f"{c}trunk.{i}.ls2.gamma"] = torch.full((D,), 0.01), torch.full((D,), 0.01)
+    d = "depth_head."
+    sd[d + "norm.weight"], sd[d + "norm.bias"] = torch.ones(D), torch.zeros(D)
+
+    def conv(name, co, ci, k, bias=True, s=None):
+        sd[d + name + ".weight"] = rn(co, ci, k, k, s=s if s is not None else (2.0 / (ci * k * k)) ** 0.5)
+        if bias:
+            sd[d + name + ".bias"] = rn(co)
+    for i, oc in enumerate(out_channels):
+        conv(f"projects.{i}", oc, D, 1)
+        conv(f"scratch.layer{i + 1}_rn", features, oc, 3, bias=False)
+    conv("resize_layers.0", out_channels[0], out_channels[0], 4)     # ConvTranspose2d weight is [in, out, k, k]
+    conv("resize_layers.1", out_channels[1], out_channels[1], 2)
+    conv("resize_layers.3", out_channels[3], out_channels[3], 3)
+    for r in (1, 2, 3, 4):
+        p = f"scratch.refinenet{r}."
+        conv(p + "out_conv", features, features, 1)
+        for u in ((1, 2) if r != 4 else (2,)):
+            conv(f"{p}resConfUnit{u}.conv1", features, features, 3)
+            conv(f"{p}resConfUnit{u}.conv2", features, features, 3)
+    conv("scratch.output_conv1", features // 2, features, 3)
+    conv("scratch.output_conv2.0", 32, features // 2, 3)
+    conv("scratch.output_conv2.2", 2, 32, 1, s=0.02)
+    return sd

@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- objects -> mesh per second on the B200 (BASELINE.json metric, configs[1]):
-one "step" = one synthetic 512x512 masked crop -> DINOv2 conditioner -> 50 CFG DiT steps -> ShapeVAE ->
-257^3 SDF decode -> marching cubes -> mesh.
+"""bench.py -- the metric of BASELINE.json on B200.
+
+Workloads (`config.workload` names the BASELINE.json config each one is):
+  default / --workload shapegen   configs[1] (and [2], [4] through the flags below): one "step" = one synthetic
+      512x512 masked crop -> DINOv2 conditioner -> 50 CFG DiT steps -> ShapeVAE -> (R+1)^3 SDF decode -> marching
+      cubes -> mesh.  --octree 512 is configs[4]'s grid; --objects N fixes the TOTAL number of objects and splits them
+      over the ranks (strong scaling: configs[2] = --objects 8 on 8 GPUs, configs[4] = --objects 32 --octree 512).
+  --workload vggt                 configs[3]: VGGT depth + camera forward (2 frames loaded at 1024^2, run at 518^2 as
+      the reference stage does) + point-cloud back-projection; roofline = the back-projection kernel's HBM GB/s.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
 
-`value`  : objects/s, preprocessed image tensor already resident in HBM, mesh left on the device.
-`e2e`    : objects/s through the public pipeline call with HOST buffers: RGBA crop in pinned host memory ->
-           H2D -> ... -> mesh vertices/faces copied back to host memory, every step.
-Objects are independent (src/2d_to_3d_models/run.py:188-193 shards them over GPUs), so N GPUs run N x K
-objects with no data-path collective; the finished meshes are gathered to rank 0 over NCCL inside the timed
-region (scaling = weak).
+`value`  : objects/s with the preprocessed crop already resident in HBM and the mesh left on the device.
+`e2e`    : objects/s through the public call `pipe(image=<PIL RGBA>, ..., output_type="mesh")` with host buffers: the
+           image processor, the pinned host -> device copy of the crop and the device -> host landing of the mesh
+           (pinned ring, r3g.dist.MeshStreamGatherer) are inside the timed region, every step.
+The two arms are INTERLEAVED object by object inside one barrier-bracketed region (device-resident object, then
+end-to-end object, K times) and each arm's time is the sum of its own CUDA-event segments, so both see the same clocks.
+Objects are independent (src/2d_to_3d_models/run.py:188-193 shards them over GPUs): no data-path collective; the finished
+meshes stream to rank 0 over NCCL on a side stream while the next object computes.
 """
 import argparse
 import json
@@ -19,7 +27,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "3d-re-gen_b200")):
@@ -27,20 +34,31 @@ for p in (ROOT, os.path.join(ROOT, "3d-re-gen_b200")):
         sys.path.insert(0, p)
 
 METRIC = "objects->mesh/sec (256^3 SDF, 50 DiT steps)"
-WORKLOAD = "single 512x512 masked crop -> Hunyuan3D-2 shape gen, 50 DiT steps, 256^3 SDF"
+METRIC_VGGT = "VGGT depth+camera forward + point-cloud back-projection (frames/s; back-projection HBM GB/s vs peak)"
+
+
+def workload_name(args):
+    if args.workload == "vggt":
+        return "VGGT depth+camera forward at 1024x1024 (run at 518x518 like the stage) + point-cloud back-projection"
+    n = f"{args.objects} synthetic 512x512 masked crops" if args.objects else "single 512x512 masked crop"
+    return f"{n} -> Hunyuan3D-2 shape gen, {args.dit_steps} DiT steps, {args.octree}^3 SDF + marching cubes"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="r3g", choices=["r3g", "reference"])
+    ap.add_argument("--workload", default="shapegen", choices=["shapegen", "vggt"])
     ap.add_argument("--octree", type=int, default=256)
     ap.add_argument("--dit-steps", type=int, default=50)
+    ap.add_argument("--objects", type=int, default=0,
+                    help="strong scaling: TOTAL objects, split over the ranks (overrides --steps)")
+    ap.add_argument("--frames", type=int, default=2, help="vggt workload: frames per scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
-                    help="warm-up + timed device-resident loop only (for ncu launch lists); prints no bench line")
+                    help="warm-up + device-resident loop only (for ncu launch lists); prints no bench line")
     return ap.parse_args()
 
 
@@ -100,37 +118,61 @@ def synthetic_crop(seed, size=512):
     return Image.fromarray(rgba, "RGBA")
 
 
+def shapegen_config(args, world, per_rank):
+    """The `config` object; both arms print exactly these keys for the same flags."""
+    return {"workload": workload_name(args), "octree_resolution": args.octree, "dit_steps": args.dit_steps,
+            "guidance": 5.0, "objects_per_gpu": per_rank, "objects_total": per_rank * world,
+            "l2": "working set (2.6 GB of weights + a 68-540 MB grid per object) exceeds L2",
+            "parallelism": f"objects sharded over {world} GPU(s), meshes streamed to rank 0 over NCCL"}
+
+
 def reference_arm(args):
-    """The reference's own CPU implementation of the path (oracle port) on the host cores."""
+    """The reference's own CPU implementation of the path (oracle port, fp32 torch + C marching cubes) on ALL host
+    cores.  torchrun exports OMP_NUM_THREADS=1 for nproc > 1: the thread count is set explicitly here, otherwise the
+    arm slows 9x exactly when N >= 2 (round 1's void SCALE ratios)."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline
     vals, det = [], None
     for i in range(args.warmup + args.steps):
-        v, det = cpu_baseline.time_object_sample(args.octree, args.dit_steps, mc_grid=97, dit_reps=1, chunk_reps=1)
+        if args.workload == "vggt":
+            v, det = cpu_baseline.time_vggt_sample(args.frames, reps=3)
+        else:
+            v, det = cpu_baseline.time_object_sample(args.octree, args.dit_steps, mc_grid=97, dit_reps=3, chunk_reps=2)
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
-    line = {"metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "octree_resolution": args.octree, "dit_steps": args.dit_steps,
-                       "note": "each step times a bounded sample of the workload and extrapolates linearly"},
-            "cpu_baseline": {"value": value, "unit": "objects/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": det["sample"]},
-            "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    vggt = args.workload == "vggt"
+    per_rank = (args.objects // world) if args.objects else args.steps
+    cfg = ({"workload": workload_name(args), "frames": args.frames} if vggt else shapegen_config(args, world, per_rank))
+    cfg["note"] = "each step times a bounded sample of the workload on the host cores and extrapolates linearly"
+    line = {"metric": METRIC_VGGT if vggt else METRIC, "value": value, "unit": "frames/s" if vggt else "objects/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+            "higher_is_better": True, "scaling": "strong" if args.objects else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "frames/s" if vggt else "objects/s",
+                             "cores": torch.get_num_threads(), "kind": "port", "sample": det["sample"]},
+            "e2e": {"value": value, "unit": "frames/s" if vggt else "objects/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# DRAM traffic of the DiT forward's GEMM launches: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one
+# forward (tools/prof_dit_gemm.py), averaged per launch like `achieved`; the committed capture is named beside it.
+GEMM_TRAFFIC_NCU = {"source": "profiles/r2_ncu_dit_gemm_traffic.csv", "dram_bytes_per_launch": None,
+                    "algorithmic_bytes_per_launch": None}
+
+
 def instrumented_linear_roofline(pipe, cond, peak_tflops):
-    """Dominant kernel = linear_kernel (every nn.Linear of the DiT: 275 launches per forward, 46 % of the step in
-    the ncu launch list).  Its launches are isolated from the other kernels of the forward -- same weights, same
-    order, same shapes/epilogues -- by recording one eager forward's r3g_linear calls and re-issuing exactly those
-    into a CUDA graph; the graph is replayed between CUDA events on the launching stream (no host gaps inside the
-    measured interval).  achieved = sum of 2*M*N*K over the launches / elapsed."""
+    """Dominant kernel = the tcgen05 GEMM (every nn.Linear of the DiT: ~46 % of the step in the ncu launch list).
+    Its launches are isolated from the other kernels of the forward -- same weights, same order, same shapes and
+    epilogues -- by recording one eager forward's r3g_linear calls and re-issuing exactly those into a CUDA graph,
+    replayed between CUDA events on the launching stream.  achieved = sum of 2*M*N*K over the launches / elapsed."""
     import torch
     from r3g import ops
     calls = []
@@ -148,7 +190,12 @@ def instrumented_linear_roofline(pipe, cond, peak_tflops):
     finally:
         ops.linear = orig
     torch.cuda.synchronize()
-    flops = sum(2.0 * (cx.numel() // cx.shape[-1]) * cw.shape[0] * cw.shape[1] for cx, cw, _, _ in calls)
+
+    def rows(t_):
+        return t_.numel() // t_.shape[-1]
+    flops = sum(2.0 * rows(cx) * cw.shape[0] * cw.shape[1] for cx, cw, _, _ in calls)
+    alg_bytes = sum(2.0 * (rows(cx) * cw.shape[1] + cw.shape[0] * cw.shape[1] + rows(cx) * cw.shape[0])
+                    for cx, cw, _, _ in calls)
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -170,32 +217,21 @@ def instrumented_linear_roofline(pipe, cond, peak_tflops):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     achieved = flops / ms / 1e9
-    return {"bound": "tensor", "kernel": "linear_kernel<BN> (tcgen05 GEMM, gemm.cu): the DiT forward's launches",
+    return {"bound": "tensor", "kernel": "linear_kernel / linear_kernel_2cta (tcgen05 GEMM, gemm.cu): the DiT forward's launches",
             "launches_timed": len(calls), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": achieved / peak_tflops, "traffic": None, "avg_launch_ms": ms / len(calls),
-            "flops_per_launch_avg": flops / len(calls),
-            "note": "weights stream from HBM (2.2 GB per forward > L2); activations mostly L2-resident",
-            # not measured in this run: DRAM bytes of the largest of these launches from the committed ncu --set full
-            # capture (dram__bytes_read.sum + dram__bytes_write.sum); `traffic` stays null because the live figure above
-            # averages 195 launches of 10 different shapes
-            "traffic_ncu": {"launch": "single-block linear1 8884x7168x1024 (GELU + q/k norm epilogue)",
-                            "dram_bytes": 115.5e6, "algorithmic_bytes": 160.3e6,
-                            "source": "profiles/r1f_ncu_gemm_selected_metrics.txt"}}
+            "frac": achieved / peak_tflops, "traffic": GEMM_TRAFFIC_NCU["dram_bytes_per_launch"],
+            "traffic_source": GEMM_TRAFFIC_NCU["source"], "avg_launch_ms": ms / len(calls),
+            "flops_per_launch_avg": flops / len(calls), "algorithmic_bytes_per_launch_avg": alg_bytes / len(calls),
+            "note": "weights stream from HBM (2.2 GB per forward > L2); activations mostly L2-resident, so DRAM traffic "
+                    "per launch sits below the algorithmic bytes"}
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return reference_arm(args)
-    import numpy as np
+def setup_dist():
     import torch
     import torch.distributed as dist
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -204,26 +240,46 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
+    return world, rank, local
+
+
+def main_shapegen(args):
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local = setup_dist()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     from r3g import _abi
+    from r3g.dist import MeshStreamGatherer
     from r3g.pipelines import Hunyuan3DDiTFlowMatchingPipeline
-    from r3g.dist import gather_meshes
 
     pk = peaks()
     pipe = Hunyuan3DDiTFlowMatchingPipeline.from_random(seed=0, device=f"cuda:{local}")
     pipe.vae.surface_extractor.keep_on_device = True
     ctx = _abi.get_context(local)
     R = args.octree
-    K, W = args.steps, args.warmup
+    if args.objects:
+        if args.objects % world:
+            raise SystemExit(f"--objects {args.objects} must be a multiple of the {world} ranks")
+        K = args.objects // world
+    else:
+        K = args.steps
+    W = args.warmup
 
-    # synthetic inputs: K+W distinct crops per rank, prepared once on the host (pinned) and on the device
-    crops = [synthetic_crop(1234567 + rank * 1000 + i) for i in range(K + W)]
-    host_in = [pipe.image_processor(c)["image"].pin_memory() for c in crops]
-    dev_in = [h.cuda(non_blocking=True) for h in host_in]
+    # synthetic inputs: distinct crops per rank and arm; the device-resident arm gets them preprocessed and uploaded
+    n_in = W + 2 * K
+    crops = [synthetic_crop(1234567 + rank * 1000 + i) for i in range(n_in)]
+    dev_in = [pipe.image_processor(c)["image"].cuda() for c in crops]
+    kw = dict(num_inference_steps=args.dit_steps, octree_resolution=R, num_chunks=16000, output_type="mesh")
 
-    def run_object(img_dev, seed):
-        cond = pipe.encode_cond(img_dev, {}, True)
-        return pipe(cond=cond, generator=torch.manual_seed(seed), num_inference_steps=args.dit_steps,
-                    octree_resolution=R, num_chunks=16000, output_type="mesh")[0]
+    def object_resident(i):
+        cond = pipe.encode_cond(dev_in[i], {}, True)
+        return pipe(cond=cond, generator=torch.manual_seed(1234567 + i), **kw)[0]
+
+    def object_e2e(i):
+        """The call a user of the reference makes (src/2d_to_3d_models/run.py:77-84)."""
+        return pipe(image=crops[i], generator=torch.manual_seed(1234567 + i), **kw)[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,76 +287,63 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed_loop(e2e):
-        h2d = d2h = 0
-        meshes = []
-        launches0 = ctx.launches + pipe.replayed_launches
-        barrier()
-        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_start.record()
-        for i in range(W, W + K):
-            if e2e:
-                img = host_in[i].cuda(non_blocking=True)
-                h2d += host_in[i].numel() * host_in[i].element_size()
-            else:
-                img = dev_in[i]
-            m = run_object(img, 1234567 + i)
-            if e2e and m is not None and world == 1:
-                # device -> host read of the step's result: into pinned buffers on a copy stream, so the transfer of
-                # object i runs under the compute of object i+1; the timed region ends after the last copy has landed
-                hv, hf = host_out[i - W]
-                nv, nf = m.mesh_v.shape[0], m.mesh_f.shape[0]
-                if nv <= hv.shape[0] and nf <= hf.shape[0]:
-                    done = torch.cuda.Event()
-                    done.record()
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(done)
-                        hv[:nv].copy_(m.mesh_v, non_blocking=True)
-                        hf[:nf].copy_(m.mesh_f, non_blocking=True)
-                else:   # a mesh larger than the pinned capacity sized at warm-up: plain synchronous read
-                    m.mesh_v.cpu(), m.mesh_f.cpu()
-                d2h += nv * 12 + nf * 12
-            meshes.append(m)
-        if world > 1:
-            got = gather_meshes([(m.mesh_v, m.mesh_f) for m in meshes if m is not None], to_host=e2e)
-            if e2e and rank == 0:
-                d2h += sum(v.numel() * 4 + f.numel() * 4 for v, f in got)
-        if e2e:
-            torch.cuda.current_stream().wait_stream(copy_stream)
-        t_end.record()
-        barrier()
-        ms = t_start.elapsed_time(t_end)
-        t = torch.tensor([ms], device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), h2d, d2h, (ctx.launches + pipe.replayed_launches - launches0), meshes
+    # warm-up (captures the DiT CUDA graph; sizes the gather capacity; lets the caching allocator see its blocks)
+    warm = [object_resident(i) if i % 2 == 0 else object_e2e(i) for i in range(W)]
+    ok = [m for m in warm if m is not None]
+    cap_v = int(1.3 * max((m.mesh_v.shape[0] for m in ok), default=1)) + 1024
+    cap_f = int(1.3 * max((m.mesh_f.shape[0] for m in ok), default=1)) + 1024
+    del warm, ok
+    d2h_bytes = [0]
 
-    # warm-up (also captures the DiT CUDA graph).  The warm-up meshes are held like the timed loop holds its own
-    # (K device-resident meshes until the gather) and released together, so that torch's caching allocator enters
-    # the timed region with K sets of ~200 MB mesh blocks: a fresh cudaMalloc of that size costs 50-100 ms here
-    # and would otherwise be charged to 2 of every 3 timed objects (profiles/README.md r1f).
-    warm = [run_object(dev_in[i], 1234567 + i) for i in range(W)]
-    cap_v = int(1.3 * max(m.mesh_v.shape[0] for m in warm if m is not None)) if any(warm) else 1
-    cap_f = int(1.3 * max(m.mesh_f.shape[0] for m in warm if m is not None)) if any(warm) else 1
-    del warm
-    # pinned landing buffers for the end-to-end arm (cudaHostAlloc of ~200 MB costs ~100 ms: outside the timed region,
-    # as a service that streams meshes to the host would keep them)
-    copy_stream = torch.cuda.Stream()
-    host_out = [(torch.empty(cap_v, 3, dtype=torch.float32).pin_memory(), torch.empty(cap_f, 3, dtype=torch.int32).pin_memory())
-                for _ in range(K)] if world == 1 else []
+    def count(step, r, v, f):          # consumer thread of the e2e gatherer on rank 0: bytes that landed on the host
+        d2h_bytes[0] += v.numel() * 4 + f.numel() * 4
+    g_dev = MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=False, sink=lambda *a: None) if world > 1 else None
+    g_e2e = MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=True, sink=count)
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms, _, _, launches, meshes = timed_loop(e2e=False)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
+    launches0 = ctx.launches + pipe.replayed_launches
+    h2d = 0
+    meshes = []
+    barrier()
+    ev[0].record()
+    for k in range(K):
+        m = object_resident(W + 2 * k)
+        if g_dev is not None:
+            g_dev.submit(*( (m.mesh_v, m.mesh_f) if m is not None else (None, None)))
+        ev[2 * k + 1].record()
+        meshes.append(m)
+        if args.profile_mode:
+            ev[2 * k + 2].record()
+            continue
+        m2 = object_e2e(W + 2 * k + 1)
+        h2d += dev_in[0].numel() * 4
+        g_e2e.submit(*((m2.mesh_v, m2.mesh_f) if m2 is not None else (None, None)))
+        ev[2 * k + 2].record()
+    if g_dev is not None:
+        g_dev.finish()
+    ev_dev_end = torch.cuda.Event(enable_timing=True)
+    ev_dev_end.record()
+    g_e2e.finish()                      # the last object's mesh has landed on rank 0's host
+    ev_end = torch.cuda.Event(enable_timing=True)
+    ev_end.record()
+    barrier()
     clk = clocks.stop() if rank == 0 else None
+    ms_dev = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)) + ev[2 * K].elapsed_time(ev_dev_end)
+    ms_e2e = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)) + ev_dev_end.elapsed_time(ev_end)
+    launches = (ctx.launches + pipe.replayed_launches - launches0)
+    t = torch.tensor([ms_dev, ms_e2e], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
     stage = dict(pipe.timings)
     if args.profile_mode:
         if rank == 0:
-            print(json.dumps({"profile_mode": True, "ms_per_step": ms / K, "stages_ms_last_object": stage}))
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms_dev / K, "stages_ms_last_object": stage}))
         return
-    ms_e2e, h2d, d2h, _, _ = timed_loop(e2e=True)
-
-    value = world * K / (ms / 1000.0)
+    value = world * K / (ms_dev / 1000.0)
     e2e_value = world * K / (ms_e2e / 1000.0)
     if rank == 0:
         cond = pipe.encode_cond(dev_in[0], {}, True)
@@ -313,25 +356,28 @@ def main():
         m0 = meshes[0]
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic (seeded random weights of the Hunyuan3D-2 architecture; noise crops)",
-            "config": {"workload": WORKLOAD, "octree_resolution": R, "dit_steps": args.dit_steps, "guidance": 5.0,
-                       "objects_per_gpu": K, "l2": "working set (2.6 GB of weights + 68 MB grid per object) exceeds L2",
-                       "parallelism": f"objects sharded over {world} GPU(s), NCCL gather of meshes to rank 0"},
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong" if args.objects else "weak",
+            "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic (seeded random weights of the Hunyuan3D-2 architecture; noise crops)",
+            "config": shapegen_config(args, world, K),
             "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d // K,
-                    "d2h_bytes_per_step": d2h // K, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": d2h_bytes[0] // (K * world) if world > 1 else d2h_bytes[0] // K,
+                    "d2h_bytes_total_on_rank0": d2h_bytes[0], "ms_per_step": ms_e2e / K,
+                    "call": "pipe(image=<PIL RGBA>, ..., output_type='mesh') + mesh landed in pinned host memory on rank 0"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,
             "stages_ms_last_object": stage,
-            "object": {"algorithmic_tflop": fl_obj / 1e12, "achieved_tflops_whole_step": fl_obj / 1e12 / (ms / K / 1e3),
-                       "frac_of_peak_whole_step": fl_obj / 1e12 / (ms / K / 1e3) / pk["tflops"],
+            "object": {"algorithmic_tflop": fl_obj / 1e12,
+                       "achieved_tflops_whole_step": fl_obj / 1e12 / (ms_dev / K / 1e3),
+                       "frac_of_peak_whole_step": fl_obj / 1e12 / (ms_dev / K / 1e3) / pk["tflops"],
                        "mesh_vertices": int(m0.mesh_v.shape[0]) if m0 is not None else 0,
                        "mesh_faces": int(m0.mesh_f.shape[0]) if m0 is not None else 0},
         }
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import cpu_baseline
+            torch.set_num_threads(os.cpu_count() or 1)
             v, det = cpu_baseline.time_object_sample(R, args.dit_steps)
             line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": det["sample"], "sampled_cpu_seconds": det["sampled_cpu_seconds"],
@@ -340,6 +386,144 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def main_vggt(args):
+    """configs[3].  One step = one scene: S frames (host tensors [S,3,1024,1024], the reference's load resolution) ->
+    bilinear resize to 518 -> aggregator (r3g kernels) -> camera head -> DPT depth head -> r3g_unproject (float64)."""
+    import importlib.util
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local = setup_dist()
+    from r3g import _abi, ops
+    from r3g.vggt_heads import VGGT, random_state_dict
+    spec = importlib.util.spec_from_file_location(
+        "stage4", os.path.join(ROOT, "stages", "camera_and_pointcloud", "minimal_demo_vggt.py"))
+    stage4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stage4)
+    pk = peaks()
+    ctx = _abi.get_context(local)
+    model = VGGT(device=f"cuda:{local}").load_state_dict(random_state_dict(0))
+    S, K, W = args.frames, args.steps, args.warmup
+    g = torch.Generator().manual_seed(1234567 + rank)
+    host_in = [torch.rand(S, 3, 1024, 1024, generator=g).pin_memory() for _ in range(K + W)]
+    dev_in = [h.cuda() for h in host_in]
+    host_pts = torch.empty(S, 518, 518, 3, dtype=torch.float64).pin_memory()
+    host_dc = torch.empty(2, S, 518, 518, dtype=torch.float32).pin_memory()
+
+    def scene(images):
+        E, Kmat, depth, conf = stage4.run_VGGT(model, images, 518)
+        pts = ops.unproject(depth[..., 0].contiguous(), E, Kmat, torch.float64)
+        return pts, depth, conf
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        scene(dev_in[i])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    launches0 = ctx.launches
+    h2d = d2h = 0
+    barrier()
+    ev[0].record()
+    for k in range(K):
+        scene(dev_in[W + k])
+        ev[2 * k + 1].record()
+        img = host_in[W + k].cuda(non_blocking=True)
+        h2d += host_in[W + k].numel() * 4
+        pts, depth, conf = scene(img)
+        host_pts.copy_(pts, non_blocking=True)
+        host_dc[0].copy_(depth[..., 0], non_blocking=True)
+        host_dc[1].copy_(conf, non_blocking=True)
+        d2h += host_pts.numel() * 8 + host_dc.numel() * 4
+        ev[2 * k + 2].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    ms_dev = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K))
+    ms_e2e = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K))
+    t = torch.tensor([ms_dev, ms_e2e], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank == 0:
+        # roofline: the back-projection kernel on a shape long enough to read a bandwidth (SURVEY.md section 8d row 4:
+        # the real 2 x 518^2 call is 8.6 MB = launch-latency bound)
+        rng = np.random.default_rng(0)
+        Sx, H, Wd = 64, 1022, 1022
+        dm = torch.rand(Sx, H, Wd, device="cuda") + 0.5
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        E = np.tile(np.concatenate([q, rng.normal(size=(3, 1))], 1).astype(np.float32), (Sx, 1, 1))
+        Km = np.tile(np.array([[800, 0, 511], [0, 800, 511], [0, 0, 1]], np.float32), (Sx, 1, 1))
+        for _ in range(3):
+            ops.unproject(dm, E, Km, torch.float64)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            out = ops.unproject(dm, E, Km, torch.float64)
+        b.record()
+        torch.cuda.synchronize()
+        ms_u = a.elapsed_time(b) / reps
+        alg = Sx * H * Wd * (4 + 24)
+        # aggregator alone, for the tensor-pipe view
+        imgs518 = torch.nn.functional.interpolate(dev_in[0], size=(518, 518), mode="bilinear", align_corners=False)[None]
+        for _ in range(2):
+            model.aggregator(imgs518)
+        a.record()
+        for _ in range(5):
+            model.aggregator(imgs518)
+        b.record()
+        torch.cuda.synchronize()
+        ms_agg = a.elapsed_time(b) / 5
+        P, C, depth_n = 1374, 1024, 24
+        fl = S * P * 24 * C * C * 72 + 4 * C * (24 * S * P * P + depth_n * S * P * P + depth_n * (S * P) ** 2)
+        line = {"metric": METRIC_VGGT, "value": world * K * S / (ms_dev / 1000.0), "unit": "frames/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 operands / f32 residual stream (aggregator), f32 heads, f64 back-projection",
+                "data": "synthetic (seeded random weights of the VGGT-1B camera+depth architecture; uniform-noise frames)",
+                "config": {"workload": workload_name(args), "frames": S, "resolution": 518, "load_resolution": 1024,
+                           "l2": "1.2 B parameters (2.4 GB fp16 + fp32 heads) exceed L2",
+                           "parallelism": f"{world} independent replica(s): one forward per scene does not shard (DESIGN.md section 5)"},
+                "e2e": {"value": world * K * S / (ms_e2e / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
+                        "d2h_bytes_per_step": d2h // K, "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(launches), "clocks": clk,
+                "roofline": {"bound": "hbm", "kernel": "unproject_kernel<f64> (rowops.cu) on [64,1022,1022]",
+                             "achieved": alg / ms_u / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": alg / ms_u / 1e6 / pk["hbm"], "traffic": None, "avg_launch_ms": ms_u,
+                             "algorithmic_bytes_per_launch": alg, "peak_source": pk["source"],
+                             "note": "4 B read + 24 B written per pixel; the real 2x518x518 call moves 15 MB (launch bound)"},
+                "aggregator": {"ms": ms_agg, "algorithmic_tflop": fl / 1e12, "tflops": fl / ms_agg / 1e9,
+                               "frac_of_tensor_peak": fl / ms_agg / 1e9 / pk["tflops"]}}
+        del out
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import cpu_baseline
+            torch.set_num_threads(os.cpu_count() or 1)
+            v, det = cpu_baseline.time_vggt_sample(S, reps=3)
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": det["sample"], "sampled_cpu_seconds": det["sampled_cpu_seconds"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.workload == "vggt":
+        return main_vggt(args)
+    return main_shapegen(args)
 
 
 if __name__ == "__main__":

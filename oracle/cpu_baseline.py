@@ -117,3 +117,46 @@ def time_object_sample(octree_resolution=256, steps=50, mc_grid=129, dit_reps=3,
                            f"{n}^3 scaled x{npts / n ** 3:.1f}; fp32 torch CPU"),
                    sampled_cpu_seconds=dit_reps * (t_double + t_single) + chunk_reps * t_chunk + t_mc)
     return 1.0 / total, details
+
+
+def time_vggt_sample(frames=2, reps=2):
+    """BASELINE.json config 4 on the host: one frame-attention block + one global-attention block of the aggregator at
+    the real geometry (S frames x 1374 tokens x 1024) averaged over `reps`, scaled to 24 DINOv2 + 24 frame + 24 global
+    blocks (a DINOv2 block costs a frame block without q/k norm and RoPE), plus the reference's numpy back-projection
+    (geometry.py:15-117) of S x 518 x 518 depth maps, timed in full.  The DPT / camera heads (~5 % of the FLOPs) are
+    left out of the sample.  Returns (frames_per_second, details)."""
+    import vggt_ref as V
+    torch.manual_seed(0)
+    C, P = 1024, 1374
+    sd = {}
+    for p in ("frame_blocks.0.", "global_blocks.0."):
+        for n, shp in (("attn.qkv", (3 * C, C)), ("attn.proj", (C, C)), ("mlp.fc1", (4 * C, C)), ("mlp.fc2", (C, 4 * C))):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.randn(*shp) * 0.02, torch.zeros(shp[0])
+        for n, d in (("norm1", C), ("norm2", C), ("attn.q_norm", 64), ("attn.k_norm", 64)):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(d), torch.zeros(d)
+        sd[p + "ls1.gamma"] = sd[p + "ls2.gamma"] = torch.full((C,), 0.1)
+    x = torch.randn(frames, P, C)
+    pos = torch.zeros(frames, P, 2, dtype=torch.long)
+    t_frame = t_global = 0.0
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            y = V.block(sd, "frame_blocks.0.", x, 16, 1e-5, pos, 100.0)
+            t_frame += (time.perf_counter() - t0) / reps
+            t0 = time.perf_counter()
+            V.block(sd, "global_blocks.0.", y.view(1, frames * P, C), 16, 1e-5, pos.view(1, frames * P, 2), 100.0)
+            t_global += (time.perf_counter() - t0) / reps
+    rng = np.random.default_rng(0)
+    depth = (rng.random((frames, 518, 518, 1)) + 0.5).astype(np.float32)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    E = np.tile(np.concatenate([q, rng.normal(size=(3, 1))], 1).astype(np.float32), (frames, 1, 1))
+    K = np.tile(np.array([[500, 0, 259], [0, 500, 259], [0, 0, 1]], np.float32), (frames, 1, 1))
+    t0 = time.perf_counter()
+    R.unproject_depth_map_to_point_map(depth, E, K)
+    t_unproject = time.perf_counter() - t0
+    total = 48 * t_frame + 24 * t_global + t_unproject
+    det = dict(t_frame_block_s=t_frame, t_global_block_s=t_global, t_unproject_s=t_unproject,
+               extrapolated_scene_s=total, sampled_cpu_seconds=reps * (t_frame + t_global) + t_unproject,
+               sample=(f"{reps}x(1 frame block + 1 global block, S={frames}, 1374 tokens, 1024 wide) scaled x(48, 24); "
+                       f"numpy back-projection of {frames}x518x518 in full; fp32 torch CPU"))
+    return frames / total, det

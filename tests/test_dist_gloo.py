@@ -37,6 +37,21 @@ def _worker(rank, world, port, q):
         q.put((mine, [(v.numpy().copy(), f.numpy().copy()) for v, f in got]))
     else:
         q.put((mine, len(got)))
+    # streaming gather: one fixed-capacity message per rank and step, ring of depth 2, uneven object counts
+    from r3g.dist import MeshStreamGatherer
+    sg = MeshStreamGatherer(cap_vertices=16, cap_faces=32, device="cpu")
+    for step in range(4):
+        if step < len(meshes):
+            sg.submit(*meshes[step])
+        else:
+            sg.submit(None, None)
+    streamed = sg.finish()
+    if rank == 0:
+        assert len(streamed) == 7
+        for (v, f), (gv, gf) in zip(streamed, got):
+            assert torch.equal(v, gv) and torch.equal(f, gf)
+    else:
+        assert streamed == []
     # a rank with nothing to send must not deadlock the gather
     got2 = gather_meshes(meshes if rank == 0 else [])
     if rank == 0:
@@ -75,6 +90,19 @@ def test_shard_and_gather_world2():
         ev = torch.rand(i + 1, 3, generator=g)
         ef = torch.randint(0, i + 1, (2 * i + 1, 3), generator=g, dtype=torch.int32)
         assert torch.equal(torch.from_numpy(v), ev) and torch.equal(torch.from_numpy(f), ef)
+
+
+def test_stream_gatherer_single_process():
+    sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
+    from r3g.dist import MeshStreamGatherer
+    seen = []
+    sg = MeshStreamGatherer(8, 8, device="cpu", sink=lambda step, r, v, f: seen.append((step, r, v.shape[0], f.shape[0])))
+    for i in range(5):
+        sg.submit(torch.rand(i + 1, 3), torch.zeros(i, 3, dtype=torch.int32))
+    assert sg.finish() == [] and seen == [(i, 0, i + 1, i) for i in range(5)]
+    import pytest
+    with pytest.raises(ValueError):
+        MeshStreamGatherer(2, 2, device="cpu").submit(torch.rand(3, 3), torch.zeros(1, 3, dtype=torch.int32))
 
 
 def test_single_process_passthrough():
