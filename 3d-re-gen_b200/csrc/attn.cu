@@ -191,6 +191,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();      // q / k / v come from the projection kernel before us (no trigger here: a multi-wave grid must not
+                   // let the next kernel's CTAs take SM slots from its own later waves; the implicit one at exit is used)
 
   if (warp == 4) {
     if (lane == 0) {
@@ -450,7 +452,7 @@ extern "C" int r3g_attention(r3g_ctx* ctx, const r3g_attention_args* a, void* st
     ctx->attr_done |= R3G_ATTR_ATTENTION;
   }
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->H, a->B);
-  kAttention<<<grid, kThreadsV2, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  R3G_CUDA_OK(ctx, r3g_launch_pdl(ctx, kAttention, grid, dim3(kThreadsV2), kSmemBytes, (cudaStream_t)stream, mq, mk, mv, p));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -23,6 +23,7 @@ extern "C" int r3g_create(int device, r3g_ctx** out) {
   }
   *out = ctx;
   ctx->gemm_2cta = -1;
+  ctx->pdl = -1;
   // the caller's current device is left as it was (the entry points switch to ctx->device for their own duration)
   struct Restore {
     int prev = -1;

@@ -12,6 +12,7 @@
 // (attention_blocks.py:250-261,484-494).
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <cstdio>
 #include "r3g_internal.h"
@@ -322,8 +323,11 @@ __device__ __forceinline__ int qkn_range(const LinearParams& p, int n0) {
 
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
-linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-              const LinearParams p) {
+linear_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_w0,
+              const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_w1,
+              const __grid_constant__ LinearParams p0, const __grid_constant__ LinearParams p1) {
+  // Two problems may share one persistent launch (r3g_linear_args.group_next: the img and txt streams of a
+  // DoubleStreamBlock): tiles [0, tiles0) belong to p0, the rest to p1 (p1.tiles_m == 0: no second problem).
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -337,12 +341,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k_blocks = (p.K + BK - 1) / BK;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles0 = p0.tiles_m * p0.tiles_n;
+  const int num_tiles = tiles0 + p1.tiles_m * p1.tiles_n;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x0);
+    tma_prefetch_desc(&tmap_w0);
+    if (p1.tiles_m) {
+      tma_prefetch_desc(&tmap_x1);
+      tma_prefetch_desc(&tmap_w1);
+    }
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -358,6 +366,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_trigger();   // persistent grid, one CTA per SM: the next kernel's CTAs become resident as ours retire
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -365,15 +375,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const bool second = tile >= tiles0;
+        const LinearParams& p = second ? p1 : p0;
+        const CUtensorMap* tmap_x = second ? &tmap_x1 : &tmap_x0;
+        const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
+        const int lt = second ? tile - tiles0 : tile;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int sg = tm / p.tiles_per_seg, l0 = (tm % p.tiles_per_seg) * BM;
+        const int num_k_blocks = (p.K + BK - 1) / BK;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kStageBytesA;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_3d(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
-          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN, kEvictLast);
+          tma_load_3d(sa, tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
+          tma_load_2d(sb, tmap_w, &full_bar[stage], kb * BK, tn * BN, kEvictLast);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -385,6 +401,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int num_k_blocks = ((tile >= tiles0 ? p1.K : p0.K) + BK - 1) / BK;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -417,7 +434,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     uint4* wsm = reinterpret_cast<uint4*>(epi_smem + (warp - 2) * kEpiSmemPerWarp);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const bool second = tile >= tiles0;
+      const LinearParams& p = second ? p1 : p0;
+      const int lt = second ? tile - tiles0 : tile;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int sg = tm / p.tiles_per_seg;
@@ -478,33 +498,39 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   }
 }
 
-template <int BN>
-int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
-  using C = Cfg<BN>;
+// One problem of a launch: tensor maps + kernel parameters.  tile_m = rows per tile (128, or 256 for the CTA pair),
+// box_n = rows of W one CTA fetches per k-block, bn = output columns per tile.
+struct Problem {
+  LinearParams p;
   CUtensorMap tx, tw;
+};
+
+int make_problem(r3g_ctx* ctx, const r3g_linear_args* a, int tile_m, int box_n, int bn, Problem& out) {
+  LinearParams& p = out.p;
+  memset(&p, 0, sizeof(p));
+  if (!a) return R3G_OK;   // no second problem: tiles_m = 0
   const int seg_len = a->seg_len > 0 ? a->seg_len : a->M;
   const int nseg = a->M / seg_len;
   {
     const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)seg_len, (uint64_t)nseg};
     const uint64_t strides[3] = {2, (uint64_t)a->ldx * 2, (uint64_t)(nseg > 1 ? a->x_seg_stride : seg_len) * a->ldx * 2};
     const uint32_t box[3] = {BK, BM, 1};
-    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 3, dims, strides, box);
+    int rc = r3g_make_tmap_f16(ctx, &out.tx, a->x, 3, dims, strides, box);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t strides[2] = {2, (uint64_t)a->K * 2};
-    const uint32_t box[2] = {BK, BN};
-    int rc = r3g_make_tmap_f16(ctx, &tw, a->w, 2, dims, strides, box);
+    const uint32_t box[2] = {BK, (uint32_t)box_n};
+    int rc = r3g_make_tmap_f16(ctx, &out.tw, a->w, 2, dims, strides, box);
     if (rc) return rc;
   }
-  LinearParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.bias = (const __half*)a->bias;
   p.y = a->y; p.ldy = a->ldy;
   p.seg_len = seg_len;
   p.y_seg_stride = nseg > 1 ? a->y_seg_stride : seg_len;
-  p.tiles_per_seg = (seg_len + BM - 1) / BM;
+  p.tiles_per_seg = (seg_len + tile_m - 1) / tile_m;
   p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
   p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
   p.residual = a->residual_f32 ? nullptr : (const __half*)a->residual;
@@ -516,16 +542,29 @@ int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
   p.qkn_q_w = (const __half*)a->qkn_q_w; p.qkn_q_b = (const __half*)a->qkn_q_b;
   p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
   p.tiles_m = nseg * p.tiles_per_seg;
-  p.tiles_n = (a->N + BN - 1) / BN;
+  p.tiles_n = (a->N + bn - 1) / bn;
+  return R3G_OK;
+}
+
+template <int BN>
+int launch_linear(r3g_ctx* ctx, const r3g_linear_args* a, const r3g_linear_args* b, cudaStream_t s) {
+  using C = Cfg<BN>;
+  Problem pa, pb;
+  int rc = make_problem(ctx, a, BM, BN, BN, pa);
+  if (rc) return rc;
+  rc = make_problem(ctx, b, BM, BN, BN, pb);
+  if (rc) return rc;
+  if (!b) { pb.tx = pa.tx; pb.tw = pa.tw; }
   constexpr unsigned kAttrBit = BN == 256 ? R3G_ATTR_LINEAR256 : BN == 128 ? R3G_ATTR_LINEAR128 : R3G_ATTR_LINEAR64;
   if (!(ctx->attr_done & kAttrBit)) {
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::kSmemBytes));
     ctx->attr_done |= kAttrBit;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = pa.p.tiles_m * pa.p.tiles_n + pb.p.tiles_m * pb.p.tiles_n;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  linear_kernel<BN><<<grid, kNumThreads, C::kSmemBytes, s>>>(tx, tw, p);
+  R3G_CUDA_OK(ctx, r3g_launch_pdl(ctx, linear_kernel<BN>, dim3(grid), dim3(kNumThreads), C::kSmemBytes, s, pa.tx, pa.tw,
+                                   pb.tx, pb.tw, pa.p, pb.p));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -542,8 +581,9 @@ constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kNumEpilogueW
 constexpr int BN2 = 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                   const LinearParams p) {
+linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_w0,
+                   const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_w1,
+                   const __grid_constant__ LinearParams p0, const __grid_constant__ LinearParams p1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
@@ -557,13 +597,17 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();           // rank inside the CTA pair
   const bool leader = cta_rank == 0;
-  const int num_k_blocks = (p.K + BK - 1) / BK;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles0 = p0.tiles_m * p0.tiles_n;              // tiles [0, tiles0): problem 0, the rest: problem 1
+  const int num_tiles = tiles0 + p1.tiles_m * p1.tiles_n;
   const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x0);
+    tma_prefetch_desc(&tmap_w0);
+    if (p1.tiles_m) {
+      tma_prefetch_desc(&tmap_x1);
+      tma_prefetch_desc(&tmap_w1);
+    }
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's expect_tx arrival; both CTAs' TMA bytes complete on it
       mbar_init(&empty_bar[s], 1);   // the leader's multicast tcgen05.commit
@@ -579,6 +623,8 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -586,8 +632,14 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const bool second = tile >= tiles0;
+        const LinearParams& p = second ? p1 : p0;
+        const CUtensorMap* tmap_x = second ? &tmap_x1 : &tmap_x0;
+        const CUtensorMap* tmap_w = second ? &tmap_w1 : &tmap_w0;
+        const int lt = second ? tile - tiles0 : tile;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int sg = tm / p.tiles_per_seg, l0 = (tm % p.tiles_per_seg) * 256 + (int)cta_rank * BM;
+        const int num_k_blocks = (p.K + BK - 1) / BK;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes2;
@@ -595,8 +647,8 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           // the peer only issues its loads: its bytes are accounted on the leader's barrier (a phase cannot
           // complete before they land because the leader armed it with the bytes of BOTH CTAs)
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
-          tma_load_3d_2sm(sa, &tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
-          tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
+          tma_load_3d_2sm(sa, tmap_x, &full_bar[stage], kb * BK, l0, sg, kEvictFirst);
+          tma_load_2d_2sm(sb, tmap_w, &full_bar[stage], kb * BK, tn * BN2 + (int)cta_rank * 128, kEvictLast);
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
       }
@@ -609,6 +661,7 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       uint32_t phase = 0;
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int num_k_blocks = ((tile >= tiles0 ? p1.K : p0.K) + BK - 1) / BK;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -640,7 +693,10 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint4* wsm = reinterpret_cast<uint4*>(epi_smem + (warp - 2) * kEpiSmemPerWarp);
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const bool second = tile >= tiles0;
+      const LinearParams& p = second ? p1 : p0;
+      const int lt = second ? tile - tiles0 : tile;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int sg = tm / p.tiles_per_seg;
@@ -702,43 +758,13 @@ linear_kernel_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
-  CUtensorMap tx, tw;
-  const int seg_len = a->seg_len > 0 ? a->seg_len : a->M;
-  const int nseg = a->M / seg_len;
-  {
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)seg_len, (uint64_t)nseg};
-    const uint64_t strides[3] = {2, (uint64_t)a->ldx * 2, (uint64_t)(nseg > 1 ? a->x_seg_stride : seg_len) * a->ldx * 2};
-    const uint32_t box[3] = {BK, BM, 1};
-    int rc = r3g_make_tmap_f16(ctx, &tx, a->x, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    const uint64_t strides[2] = {2, (uint64_t)a->K * 2};
-    const uint32_t box[2] = {BK, 128};
-    int rc = r3g_make_tmap_f16(ctx, &tw, a->w, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  LinearParams p;
-  p.M = a->M; p.N = a->N; p.K = a->K;
-  p.bias = (const __half*)a->bias;
-  p.y = a->y; p.ldy = a->ldy;
-  p.seg_len = seg_len;
-  p.y_seg_stride = nseg > 1 ? a->y_seg_stride : seg_len;
-  p.tiles_per_seg = (seg_len + 255) / 256;
-  p.act = a->act; p.act_col0 = a->act_col0; p.act_col1 = a->act_col1;
-  p.gate = (const __half*)a->gate; p.gate_ld = a->gate_ld; p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
-  p.residual = a->residual_f32 ? nullptr : (const __half*)a->residual;
-  p.residual_f32 = a->residual_f32 ? (const float*)a->residual : nullptr;
-  p.ls_gamma = (const float*)a->ls_gamma;
-  p.out_f32 = a->out_f32;
-  p.qkn_mode = a->qkn_mode; p.qkn_q_col0 = a->qkn_q_col0; p.qkn_k_col0 = a->qkn_k_col0; p.qkn_cols = a->qkn_cols;
-  p.qkn_eps = a->qkn_eps;
-  p.qkn_q_w = (const __half*)a->qkn_q_w; p.qkn_q_b = (const __half*)a->qkn_q_b;
-  p.qkn_k_w = (const __half*)a->qkn_k_w; p.qkn_k_b = (const __half*)a->qkn_k_b;
-  p.tiles_m = nseg * p.tiles_per_seg;
-  p.tiles_n = a->N / BN2;
+int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, const r3g_linear_args* b, cudaStream_t s) {
+  Problem pa, pb;
+  int rc = make_problem(ctx, a, 256, 128, BN2, pa);
+  if (rc) return rc;
+  rc = make_problem(ctx, b, 256, 128, BN2, pb);
+  if (rc) return rc;
+  if (!b) { pb.tx = pa.tx; pb.tw = pa.tw; }
   if (!(ctx->attr_done & R3G_ATTR_LINEAR_2CTA)) {
     R3G_CUDA_OK(ctx, cudaFuncSetAttribute(linear_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
     ctx->attr_done |= R3G_ATTR_LINEAR_2CTA;
@@ -763,20 +789,16 @@ int launch_linear_2cta(r3g_ctx* ctx, const r3g_linear_args* a, cudaStream_t s) {
     ctx->max_clusters2 = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
     if (getenv("R3G_DEBUG_GEMM")) fprintf(stderr, "[r3g gemm] co-resident CTA pairs: %d\n", ctx->max_clusters2);
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = pa.p.tiles_m * pa.p.tiles_n + pb.p.tiles_m * pb.p.tiles_n;
   const int clusters = tiles < ctx->max_clusters2 ? tiles : ctx->max_clusters2;
-  linear_kernel_2cta<<<2 * clusters, kNumThreads, kSmemBytes2, s>>>(tx, tw, p);
+  R3G_CUDA_OK(ctx, r3g_launch_pdl(ctx, linear_kernel_2cta, dim3(2 * clusters), dim3(kNumThreads), kSmemBytes2, s, pa.tx,
+                                   pa.tw, pb.tx, pb.tw, pa.p, pb.p));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
 
-}  // namespace
-
-extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) {
-  if (!ctx || !ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "linear: no CUDA device (there is no CPU fallback)");
-  if (!a || !a->x || !a->w || !a->y) return r3g_fail(ctx, R3G_E_INVALID, "linear: null argument");
-  r3g_device_guard guard(ctx);
-  if (a->M <= 0) return R3G_OK;
+int validate_linear(r3g_ctx* ctx, const r3g_linear_args* a) {
+  if (!a->x || !a->w || !a->y) return r3g_fail(ctx, R3G_E_INVALID, "linear: null argument");
   if (a->N % 32 || a->K % 8 || a->ldx % 8 || a->ldy % 8)
     return r3g_fail(ctx, R3G_E_INVALID, "linear: need N %% 32 == 0, K %% 8 == 0, ldx/ldy %% 8 == 0 (N=%d K=%d)", a->N,
                     a->K);
@@ -799,12 +821,28 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
     if (overlaps(a->qkn_q_col0) || (k_on && overlaps(a->qkn_k_col0)))
       return r3g_fail(ctx, R3G_E_INVALID, "linear: normalised columns must lie outside the activation range");
   }
+  return R3G_OK;
+}
+
+}  // namespace
+
+extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) {
+  if (!ctx || !ctx->encode_tiled) return r3g_fail(ctx, R3G_E_CUDA, "linear: no CUDA device (there is no CPU fallback)");
+  if (!a) return r3g_fail(ctx, R3G_E_INVALID, "linear: null argument");
+  r3g_device_guard guard(ctx);
+  const r3g_linear_args* b = (const r3g_linear_args*)a->group_next;
+  if (b && b->group_next) return r3g_fail(ctx, R3G_E_INVALID, "linear: at most two problems per launch");
+  if (a->M <= 0) { a = b; b = nullptr; }
+  if (b && b->M <= 0) b = nullptr;
+  if (!a) return R3G_OK;
+  int rc = validate_linear(ctx, a);
+  if (rc) return rc;
+  if (b && (rc = validate_linear(ctx, b))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   // Tile choice: wave efficiency (tiles / (waves * units)) times a per-tile throughput factor measured on B200
-  // (CTA-pair 256x256: 1.08 for K <= 2048 else 0.93, 128x256: 1.0, 128x128: 0.7).  N = 1024 GEMMs with ~6k rows, for example, fill only
-  // 1.3 waves of 128x256 tiles but 2.6 waves of 128x128 tiles.
-  const int seg_len_ = a->seg_len > 0 ? a->seg_len : a->M;
-  const int nseg_ = a->M / seg_len_;
+  // (CTA-pair 256x256: 1.08 for K <= 2048 else 0.93, 128x256: 1.0, 128x128: 0.7), over the tiles of BOTH problems of a
+  // grouped launch.  N = 1024 GEMMs with ~6k rows, for example, fill only 1.3 waves of 128x256 tiles; the img and txt
+  // streams of a DoubleStreamBlock together (6144 + 2740 rows) fill 1.95 of 2.
   const int sms = ctx->num_sms;
   auto eff = [&](int64_t tiles, int units, double factor) {
     if (tiles <= 0) return 0.0;
@@ -815,14 +853,21 @@ extern "C" int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream) 
     const char* e = getenv("R3G_GEMM_2CTA");
     ctx->gemm_2cta = (e && e[0] == '0') ? 0 : 1;
   }
-  const int mode = ctx->gemm_2cta;
-  const int64_t tm128 = (int64_t)nseg_ * ((seg_len_ + 127) / 128), tm256 = (int64_t)nseg_ * ((seg_len_ + 255) / 256);
+  auto tiles_of = [&](const r3g_linear_args* q, int tm, int tn) -> int64_t {
+    if (!q) return 0;
+    const int seg = q->seg_len > 0 ? q->seg_len : q->M;
+    return (int64_t)(q->M / seg) * ((seg + tm - 1) / tm) * ((q->N + tn - 1) / tn);
+  };
+  const int n_min = b ? (a->N < b->N ? a->N : b->N) : a->N;
+  const int k_max = b ? (a->K > b->K ? a->K : b->K) : a->K;
+  const bool n256 = a->N % 256 == 0 && (!b || b->N % 256 == 0);
   // measured: the CTA-pair tile wins for short K (epilogue-heavy), the single-CTA tile for K >= 4096
-  const double e2 = (mode && a->N % 256 == 0) ? eff(tm256 * (a->N / 256), sms / 2, a->K <= 2048 ? 1.08 : 0.93) : 0.0;
-  const double e256 = a->N >= 256 ? eff(tm128 * ((a->N + 255) / 256), sms, 1.0) : 0.0;
-  const double e128 = a->N >= 128 ? eff(tm128 * ((a->N + 127) / 128), sms, 0.7) : 0.0;
-  if (e2 > 0.0 && e2 >= e256 && e2 >= e128) return launch_linear_2cta(ctx, a, s);
-  if (e256 > 0.0 && e256 >= e128) return launch_linear<256>(ctx, a, s);
-  if (a->N >= 128) return launch_linear<128>(ctx, a, s);
-  return launch_linear<64>(ctx, a, s);
+  const double e2 = (ctx->gemm_2cta && n256) ? eff(tiles_of(a, 256, 256) + tiles_of(b, 256, 256), sms / 2,
+                                                    k_max <= 2048 ? 1.08 : 0.93) : 0.0;
+  const double e256 = n_min >= 256 ? eff(tiles_of(a, 128, 256) + tiles_of(b, 128, 256), sms, 1.0) : 0.0;
+  const double e128 = n_min >= 128 ? eff(tiles_of(a, 128, 128) + tiles_of(b, 128, 128), sms, 0.7) : 0.0;
+  if (e2 > 0.0 && e2 >= e256 && e2 >= e128) return launch_linear_2cta(ctx, a, b, s);
+  if (e256 > 0.0 && e256 >= e128) return launch_linear<256>(ctx, a, b, s);
+  if (n_min >= 128) return launch_linear<128>(ctx, a, b, s);
+  return launch_linear<64>(ctx, a, b, s);
 }

@@ -25,6 +25,7 @@ struct r3g_ctx {
   unsigned attr_done;          // R3G_ATTR_* bits: cudaFuncSetAttribute already applied on this context's device
   int max_clusters2;           // co-resident CTA pairs of linear_kernel_2cta (0 = not queried yet)
   int gemm_2cta;               // -1 = environment not read yet; R3G_GEMM_2CTA=0 disables the CTA-pair kernel
+  int pdl;                     // -1 = environment not read yet; R3G_PDL=0 disables programmatic dependent launch
 };
 enum { R3G_ATTR_ATTENTION = 1, R3G_ATTR_LINEAR64 = 2, R3G_ATTR_LINEAR128 = 4, R3G_ATTR_LINEAR256 = 8,
        R3G_ATTR_LINEAR_2CTA = 16, R3G_ATTR_MISC0 = 32, R3G_ATTR_MISC1 = 64, R3G_ATTR_MISC2 = 128 };
@@ -69,6 +70,33 @@ static inline int r3g_fail(r3g_ctx* ctx, int code, const char* fmt, ...) {
       return r3g_fail((ctx), R3G_E_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
     (ctx)->launches++;                                                                                 \
   } while (0)
+
+// Launch of a kernel that calls pdl_wait() before its first access to memory another kernel produces (r3g_ptx.cuh):
+// with R3G_PDL != 0 it carries the programmatic-stream-serialization attribute, so its prologue overlaps the tail of
+// the previous kernel in the stream (also inside CUDA-graph capture, where the edge becomes a programmatic dependency).
+#ifdef __CUDACC__
+#include <stdlib.h>
+#include <utility>
+template <typename... KArgs, typename... Args>
+inline cudaError_t r3g_launch_pdl(r3g_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t s, Args&&... args) {
+  if (ctx->pdl < 0) {
+    const char* e = getenv("R3G_PDL");
+    ctx->pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // 2D..4D fp16 tensor map with 128B swizzle; dims/strides innermost first, strides in BYTES for dims >= 1.
 int r3g_make_tmap_f16(r3g_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

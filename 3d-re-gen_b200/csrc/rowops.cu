@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256, NCH == 4 ? 3 : 2) layernorm_kernel(const 
     }
     __syncthreads();
   }
+  pdl_wait();      // the affine weights above are constants; x (and the modulation vectors) come from earlier kernels
+  pdl_trigger();
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -416,6 +418,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __half* __restrict__ w,
                                                    __half* __restrict__ out, int64_t out_ld, int B, int N, int K,
                                                    int silu_in, int silu_out) {
   extern __shared__ float gemv_x[];   // [BT][K]
+  pdl_wait();      // vec is the previous kernel's output
+  pdl_trigger();
   for (int i = threadIdx.x; i < BT * K; i += blockDim.x) {
     const int b = i / K, k = i - b * K;
     float xv = 0.f;
@@ -604,6 +608,8 @@ __global__ void __launch_bounds__(256, NCH == 4 ? 3 : 2) lnpost_dot_kernel(const
     lp_c[2 * width + i] = h2f(w_out[i]);
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -733,13 +739,11 @@ extern "C" int r3g_layernorm(r3g_ctx* ctx, const void* x, int64_t ldx, void* y, 
   const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
   const size_t smem = (w || b) ? (size_t)2 * width * sizeof(float) : 0;
   auto go = [&](auto kern) {
-    kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, width, eps,
-                                                 (const __half*)w, (const __half*)b, (const __half*)scale,
-                                                 (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride,
-                                                 y_seg_stride);
+    return r3g_launch_pdl(ctx, kern, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y,
+                          ldy, rows, width, eps, (const __half*)w, (const __half*)b, (const __half*)scale,
+                          (const __half*)shift, mod_ld, rows_per_batch, seg_len, x_seg_stride, y_seg_stride);
   };
-  if (width <= 1024) go(layernorm_kernel<4>);
-  else go(layernorm_kernel<8>);
+  R3G_CUDA_OK(ctx, width <= 1024 ? go(layernorm_kernel<4>) : go(layernorm_kernel<8>));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -821,13 +825,11 @@ extern "C" int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const voi
   if (smem > 48 * 1024) return r3g_fail(ctx, R3G_E_INVALID, "gemv: B_pad * K * 4 bytes must fit 48 KB of shared memory");
   const unsigned grid = (unsigned)((N + 8 * kGemvRows - 1) / (8 * kGemvRows));
   auto args = [&](auto kern) {
-    kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)w, (const __half*)bias, (const __half*)vec, vec_ld,
-                                                    (__half*)out, out_ld, B, N, K, silu_in, silu_out);
+    return r3g_launch_pdl(ctx, kern, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)w,
+                          (const __half*)bias, (const __half*)vec, vec_ld, (__half*)out, out_ld, B, N, K, silu_in, silu_out);
   };
-  if (bt == 1) args(gemv_kernel<1>);
-  else if (bt == 2) args(gemv_kernel<2>);
-  else if (bt == 4) args(gemv_kernel<4>);
-  else args(gemv_kernel<8>);
+  R3G_CUDA_OK(ctx, bt == 1 ? args(gemv_kernel<1>) : bt == 2 ? args(gemv_kernel<2>) : bt == 4 ? args(gemv_kernel<4>)
+                                                                                              : args(gemv_kernel<8>));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -895,11 +897,11 @@ extern "C" int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows
   if (rows <= 0) return R3G_OK;
   const unsigned grid = (unsigned)min((rows + 7) / 8, ctx->num_sms * (width <= 1024 ? 3 : 2));
   auto go = [&](auto kern) {
-    kern<<<grid, 256, (size_t)3 * width * sizeof(float), (cudaStream_t)stream>>>((const __half*)x, ldx, rows, width, eps, (const __half*)ln_w,
-                                                 (const __half*)ln_b, (const __half*)w_out, (const __half*)b_out, out);
+    return r3g_launch_pdl(ctx, kern, dim3(grid), dim3(256), (size_t)3 * width * sizeof(float), (cudaStream_t)stream,
+                          (const __half*)x, ldx, rows, width, eps, (const __half*)ln_w, (const __half*)ln_b,
+                          (const __half*)w_out, (const __half*)b_out, out);
   };
-  if (width <= 1024) go(lnpost_dot_kernel<4>);
-  else go(lnpost_dot_kernel<8>);
+  R3G_CUDA_OK(ctx, width <= 1024 ? go(lnpost_dot_kernel<4>) : go(lnpost_dot_kernel<8>));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -31,6 +31,7 @@ class LinearArgs(C.Structure):
         ("qkn_mode", C.c_int), ("qkn_q_col0", C.c_int), ("qkn_k_col0", C.c_int), ("qkn_cols", C.c_int),
         ("qkn_eps", C.c_float),
         ("qkn_q_w", C.c_void_p), ("qkn_q_b", C.c_void_p), ("qkn_k_w", C.c_void_p), ("qkn_k_b", C.c_void_p),
+        ("group_next", C.c_void_p),
     ]
 
 

@@ -50,6 +50,7 @@ class Hunyuan3DDiT:
         self.taps = None  # set to a list to record the hidden state after every block (parity tests)
         # QKNorm inside the q/k/v projection's epilogue (r3g_linear qkn_*); False runs the separate r3g_qk_norm pass
         self.fuse_qk_norm = True
+        self.group_streams = True   # img + txt projections of a DoubleStreamBlock as one grouped launch
 
     # ------------------------------------------------------------------------------------------ weights
     def to(self, device=None, dtype=None):
@@ -194,32 +195,37 @@ class Hunyuan3DDiT:
         ops.linear(cond, w["cond_in.weight"], w["cond_in.bias"], out=txt)
 
         q4 = QKV.view(B, L, 3, nh, 64)
+        streams = (("img", img, Lt, Li), ("txt", txt, 0, Lt))
+        # the two streams' projections apply different weights to different rows of the joint buffers: one launch per
+        # PAIR (ops.linear_pair), so that 6144 + 2740 rows share the persistent grid (include/r3g.h: group_next)
+        pair = ops.linear_pair if self.group_streams else (lambda a, b: (ops.linear(**a), ops.linear(**b)))
         for i in range(self.depth):
             p = f"double_blocks.{i}."
-            for s, xs, ofs, Ls in (("img", img, Lt, Li), ("txt", txt, 0, Lt)):
+            calls = []
+            for s, xs, ofs, Ls in streams:
                 sh1, sc1, g1, sh2, sc2, g2 = self._mod(ws, (i, s), 6)
                 xm = XM[:, ofs:ofs + Ls]
                 ops.layernorm(xs, eps=1e-6, scale=sc1, shift=sh1, rows_per_batch=Ls, out=xm)
-                qkv_s = QKV[:, ofs:ofs + Ls]
                 qs, ks = w[p + f"{s}_attn.norm.query_norm.scale"], w[p + f"{s}_attn.norm.key_norm.scale"]
+                c = dict(x=xm, w=w[p + f"{s}_attn.qkv.weight"], bias=w[p + f"{s}_attn.qkv.bias"], out=QKV[:, ofs:ofs + Ls])
                 if self.fuse_qk_norm:
-                    ops.linear(xm, w[p + f"{s}_attn.qkv.weight"], w[p + f"{s}_attn.qkv.bias"], out=qkv_s,
-                               qk_norm=dict(mode=ops.QKN_RMS, q_col0=0, k_col0=H, cols=H, eps=1e-6, q_w=qs, k_w=ks))
-                else:
-                    ops.linear(xm, w[p + f"{s}_attn.qkv.weight"], w[p + f"{s}_attn.qkv.bias"], out=qkv_s)
-                    ops.qk_norm_(qkv_s, nh, 0, H, 64, 0, 1e-6, qs, None, ks, None)
+                    c["qk_norm"] = dict(mode=ops.QKN_RMS, q_col0=0, k_col0=H, cols=H, eps=1e-6, q_w=qs, k_w=ks)
+                calls.append(c)
+            pair(*calls)
+            if not self.fuse_qk_norm:
+                for s, xs, ofs, Ls in streams:
+                    ops.qk_norm_(QKV[:, ofs:ofs + Ls], nh, 0, H, 64, 0, 1e-6, w[p + f"{s}_attn.norm.query_norm.scale"], None,
+                                 w[p + f"{s}_attn.norm.key_norm.scale"], None)
             ops.attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], out=q4[:, :, 0])  # joint txt+img attention
-            for s, xs, ofs, Ls in (("img", img, Lt, Li), ("txt", txt, 0, Lt)):
+            pair(*[dict(x=QKV[:, ofs:ofs + Ls, :H], w=w[p + f"{s}_attn.proj.weight"], bias=w[p + f"{s}_attn.proj.bias"],
+                        out=xs, gate=self._mod(ws, (i, s), 6)[2], gate_rows=Ls, residual=xs) for s, xs, ofs, Ls in streams])
+            for s, xs, ofs, Ls in streams:
                 sh1, sc1, g1, sh2, sc2, g2 = self._mod(ws, (i, s), 6)
-                attn_s = QKV[:, ofs:ofs + Ls, :H]
-                ops.linear(attn_s, w[p + f"{s}_attn.proj.weight"], w[p + f"{s}_attn.proj.bias"], out=xs, gate=g1,
-                           gate_rows=Ls, residual=xs)
-                xm = XM[:, ofs:ofs + Ls]
-                ops.layernorm(xs, eps=1e-6, scale=sc2, shift=sh2, rows_per_batch=Ls, out=xm)
-                hid = HID[:, ofs:ofs + Ls]
-                ops.linear(xm, w[p + f"{s}_mlp.0.weight"], w[p + f"{s}_mlp.0.bias"], out=hid, act=ops.ACT_GELU_TANH)
-                ops.linear(hid, w[p + f"{s}_mlp.2.weight"], w[p + f"{s}_mlp.2.bias"], out=xs, gate=g2, gate_rows=Ls,
-                           residual=xs)
+                ops.layernorm(xs, eps=1e-6, scale=sc2, shift=sh2, rows_per_batch=Ls, out=XM[:, ofs:ofs + Ls])
+            pair(*[dict(x=XM[:, ofs:ofs + Ls], w=w[p + f"{s}_mlp.0.weight"], bias=w[p + f"{s}_mlp.0.bias"],
+                        out=HID[:, ofs:ofs + Ls], act=ops.ACT_GELU_TANH) for s, xs, ofs, Ls in streams])
+            pair(*[dict(x=HID[:, ofs:ofs + Ls], w=w[p + f"{s}_mlp.2.weight"], bias=w[p + f"{s}_mlp.2.bias"], out=xs,
+                        gate=self._mod(ws, (i, s), 6)[5], gate_rows=Ls, residual=xs) for s, xs, ofs, Ls in streams])
             if self.taps is not None:
                 self.taps.append(X.clone())
 

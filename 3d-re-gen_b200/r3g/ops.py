@@ -79,18 +79,10 @@ def _merge_seg(xs, ys, name):
 QKN_RMS, QKN_LAYERNORM = 1, 2
 
 
-def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
-           ls_gamma=None, out_dtype=torch.float16, qk_norm=None):
-    """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
-
-    x: [..., K] or a strided [M, K] / [S, L, K] view, w: [N, K] contiguous, out: same row structure, width N.
-    gate: [B, N] view with unit inner stride, applied to logical rows b = r // gate_rows.
-    residual must be the same view geometry as out (and may be out itself).
-    qk_norm: dict(mode=QKN_RMS|QKN_LAYERNORM, q_col0, k_col0 (None: q only), cols, eps, q_w, q_b, k_w, k_b) -- the per-head
-    q/k normalisation fused into the epilogue (see qkn_* in include/r3g.h).
-    """
+def _linear_args(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None, gate_rows=0, residual=None,
+                 ls_gamma=None, out_dtype=torch.float16, qk_norm=None):
+    """Build one r3g_linear_args; returns (struct, out tensor, tensors the struct points into)."""
     _f16(x, "x"); _f16(w, "w")
-    ctx = _ctx(x)
     x2, M, K, ldx, xl, xst = _rows(x, "x")
     N = w.shape[0]
     if w.shape[1] != K or not w.is_contiguous():
@@ -101,6 +93,7 @@ def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None,
     if No != N or Mo != M:
         raise ValueError(f"out has shape {tuple(out.shape)}, expected {M} rows x {N}")
     seg_len, xs, ys = _merge_seg((xl, xst, M), (yl, yst), "linear")
+    keep = [x2, w, bias, o2, gate, residual, ls_gamma]
     a = _abi.LinearArgs()
     a.x, a.ldx, a.w, a.bias = x2.data_ptr(), ldx, w.data_ptr(), (bias.data_ptr() if bias is not None else None)
     a.y, a.ldy = o2.data_ptr(), ldy
@@ -136,8 +129,37 @@ def linear(x, w, bias=None, *, out=None, act=ACT_NONE, act_cols=None, gate=None,
                 if t.numel() != 64 or not t.is_contiguous():
                     raise ValueError(f"qk_norm {name} must be a contiguous fp16 [64]")
                 setattr(a, "qkn_" + name, t.data_ptr())
+                keep.append(t)
+    return a, out, keep
+
+
+def linear(x, w, bias=None, **kw):
+    """Y = epilogue(X W^T + bias); see r3g_linear in include/r3g.h.
+
+    x: [..., K] or a strided [M, K] / [S, L, K] view, w: [N, K] contiguous, out: same row structure, width N.
+    gate: [B, N] view with unit inner stride, applied to logical rows b = r // gate_rows.
+    residual must be the same view geometry as out (and may be out itself).
+    qk_norm: dict(mode=QKN_RMS|QKN_LAYERNORM, q_col0, k_col0 (None: q only), cols, eps, q_w, q_b, k_w, k_b) -- the per-head
+    q/k normalisation fused into the epilogue (see qkn_* in include/r3g.h).
+    """
+    ctx = _ctx(x)
+    a, out, _keep = _linear_args(x, w, bias, **kw)
     ctx.check(ctx.lib.r3g_linear(ctx.handle, C.byref(a), _stream()))
     return out
+
+
+def linear_pair(first, second):
+    """Two independent linears in ONE launch (r3g_linear_args.group_next): `first` / `second` are dicts of linear()'s
+    arguments (x, w, bias, out, ...).  Results are those of linear(**first), linear(**second); the tiles of both problems
+    share one persistent grid -- the img and txt streams of a DoubleStreamBlock fill the machine together."""
+    ctx = _ctx(first["x"])
+    if second["x"].device != first["x"].device:
+        raise ValueError("linear_pair: both problems must live on the same device")
+    a, out_a, _ka = _linear_args(**first)
+    b, out_b, _kb = _linear_args(**second)
+    a.group_next = C.addressof(b)
+    ctx.check(ctx.lib.r3g_linear(ctx.handle, C.byref(a), _stream()))
+    return out_a, out_b
 
 
 def attention(q, k, v, out=None, scale=None):

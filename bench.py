@@ -175,37 +175,44 @@ def instrumented_linear_roofline(pipe, cond, peak_tflops):
     replayed between CUDA events on the launching stream.  achieved = sum of 2*M*N*K over the launches / elapsed."""
     import torch
     from r3g import ops
-    calls = []
-    orig = ops.linear
+    calls = []          # (function, args, kwargs) of every GEMM launch of one forward, in order
+    orig, orig_pair = ops.linear, ops.linear_pair
 
     def record(x, w, bias=None, **kw):
-        calls.append((x, w, bias, kw))
+        calls.append((orig, (x, w, bias), kw))
         return orig(x, w, bias, **kw)
+
+    def record_pair(first, second):
+        calls.append((orig_pair, (first, second), {}))
+        return orig_pair(first, second)
 
     x = torch.randn(2, pipe.vae.latent_shape[0], pipe.vae.latent_shape[1], device="cuda").half()
     t = torch.full((2,), 0.5, device="cuda", dtype=torch.float16)
-    ops.linear = record
+    ops.linear, ops.linear_pair = record, record_pair
     try:
         pipe.model(x, t, cond)
     finally:
-        ops.linear = orig
+        ops.linear, ops.linear_pair = orig, orig_pair
     torch.cuda.synchronize()
 
     def rows(t_):
         return t_.numel() // t_.shape[-1]
-    flops = sum(2.0 * rows(cx) * cw.shape[0] * cw.shape[1] for cx, cw, _, _ in calls)
-    alg_bytes = sum(2.0 * (rows(cx) * cw.shape[1] + cw.shape[0] * cw.shape[1] + rows(cx) * cw.shape[0])
-                    for cx, cw, _, _ in calls)
+
+    def problems(fn, a):
+        return [(a[0], a[1])] if fn is orig else [(d["x"], d["w"]) for d in a]
+    probs = [pw for fn, a, _ in calls for pw in problems(fn, a)]
+    flops = sum(2.0 * rows(cx) * cw.shape[0] * cw.shape[1] for cx, cw in probs)
+    alg_bytes = sum(2.0 * (rows(cx) * cw.shape[1] + cw.shape[0] * cw.shape[1] + rows(cx) * cw.shape[0]) for cx, cw in probs)
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for cx, cw, cb, kw in calls:
-            orig(cx, cw, cb, **kw)
+        for fn, a, kw in calls:
+            fn(*a, **kw)
     torch.cuda.current_stream().wait_stream(side)
     with torch.cuda.graph(g):
-        for cx, cw, cb, kw in calls:
-            orig(cx, cw, cb, **kw)
+        for fn, a, kw in calls:
+            fn(*a, **kw)
     for _ in range(3):
         g.replay()
     reps = 5
@@ -218,7 +225,7 @@ def instrumented_linear_roofline(pipe, cond, peak_tflops):
     ms = a.elapsed_time(b) / reps
     achieved = flops / ms / 1e9
     return {"bound": "tensor", "kernel": "linear_kernel / linear_kernel_2cta (tcgen05 GEMM, gemm.cu): the DiT forward's launches",
-            "launches_timed": len(calls), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "launches_timed": len(calls), "gemm_problems": len(probs), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": GEMM_TRAFFIC_NCU["dram_bytes_per_launch"],
             "traffic_source": GEMM_TRAFFIC_NCU["source"], "avg_launch_ms": ms / len(calls),
             "flops_per_launch_avg": flops / len(calls), "algorithmic_bytes_per_launch_avg": alg_bytes / len(calls),

@@ -92,6 +92,10 @@ int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, flo
  *        [qkn_q_col0, qkn_q_col0 + qkn_cols) with (qkn_q_w, qkn_q_b) and, if qkn_k_col0 >= 0, of
  *        [qkn_k_col0, qkn_k_col0 + qkn_cols) with (qkn_k_w, qkn_k_b); the weights are fp16 [64] (bias NULL in mode 1).
  *        Column offsets and qkn_cols are multiples of 64; these columns must carry no activation / gate / residual.
+ *   group_next: a second, independent problem (its own x / w / y / epilogue operands and sizes; its group_next must be
+ *        NULL) whose tiles share this call's persistent grid.  The img and txt streams of a DoubleStreamBlock apply
+ *        different weights to 6144 and 2740 rows (hunyuan3ddit.py:196-216): separately their N = 1024 projections
+ *        fill 1.3 and 0.65 waves of 256 x 256 tiles, together 1.95 of 2.  Results are those of two separate calls.
  */
 typedef struct {
   const void* x; int64_t ldx;
@@ -109,6 +113,7 @@ typedef struct {
   int qkn_mode, qkn_q_col0, qkn_k_col0, qkn_cols;
   float qkn_eps;
   const void* qkn_q_w; const void* qkn_q_b; const void* qkn_k_w; const void* qkn_k_b;
+  const void* group_next;    /* NULL, or a second r3g_linear_args executed by the SAME launch */
 } r3g_linear_args;
 int r3g_linear(r3g_ctx* ctx, const r3g_linear_args* a, void* stream);
 

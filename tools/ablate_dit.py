@@ -15,7 +15,7 @@ from r3g import ops  # noqa: E402
 from r3g.dit import Hunyuan3DDiT  # noqa: E402
 from r3g.pipelines import HUNYUAN3D_2_CONFIG  # noqa: E402
 
-FAMILIES = ["linear", "attention", "layernorm", "qk_norm_", "gemv", "timestep_embedding"]
+FAMILIES = ["linear", "linear_pair", "attention", "layernorm", "qk_norm_", "gemv", "timestep_embedding"]
 
 
 def time_graph(calls, reps=5):
@@ -48,6 +48,7 @@ def main():
     x = torch.randn(2, 3072, 64, device="cuda").half()
     t = torch.full((2,), 0.5, device="cuda", dtype=torch.float16)
     cond = {"main": torch.randn(2, 1370, 1536, device="cuda").half()}
+    model.group_streams = os.environ.get("R3G_GROUP", "1") != "0"
     model(x, t, cond)
     calls = []
     orig = {f: getattr(ops, f) for f in FAMILIES}
@@ -77,7 +78,7 @@ def main():
         out["families"][f] = {"launches": n, "minus_ms": minus, "alone_ms": alone}
         print(f, out["families"][f], flush=True)
     print(json.dumps(out))
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ablate_dit.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("R3G_ABLATE_OUT", "ablate_dit.json")), "w"), indent=1)
 
 
 if __name__ == "__main__":
