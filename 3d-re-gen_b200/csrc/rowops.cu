@@ -524,6 +524,10 @@ struct GridParams {
   int include_pi;
 };
 
+// kF32 = false: the queries are an fp16 tensor, the products x * f are fp16 arithmetic (the dense-grid path,
+// volume_decoders.py:168); kF32 = true: float32 queries (FlashVDM's refinement levels, volume_decoders.py:395-396): the
+// embedding is computed in float32 and only the result is cast to the latents' dtype (attention_blocks.py:486).
+template <bool kF32 = false>
 __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi);
 
 __global__ void __launch_bounds__(256) grid_fourier_kernel(__half* __restrict__ out, int64_t out_ld, int64_t start,
@@ -555,6 +559,15 @@ __global__ void __launch_bounds__(256) points_fourier_kernel(const __half* __res
   fourier_row(out + i * out_ld, out_ld, xh, F, include_pi);
 }
 
+__global__ void __launch_bounds__(256) points_fourier_f32_kernel(const float* __restrict__ q, __half* __restrict__ out,
+                                                                 int64_t out_ld, int64_t n, int F, int include_pi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xh[3] = {q[3 * i], q[3 * i + 1], q[3 * i + 2]};
+  fourier_row<true>(out + i * out_ld, out_ld, xh, F, include_pi);
+}
+
+template <bool kF32>
 __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const float* xh, int F, int include_pi) {
   if (F == 8 && out_ld == 64 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
     // the geo-decoder's shape: the 51 features + 13 zeros of a row are built in registers and leave as eight
@@ -572,7 +585,7 @@ __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const flo
       for (int k = 0; k < 8; ++k) {
         float f = (float)(1 << k);
         if (include_pi) f = rnd_h(f * 3.14159265358979323846f);
-        const float e = rnd_h(xh[d] * f);
+        const float e = kF32 ? xh[d] * f : rnd_h(xh[d] * f);
         r[3 + d * 8 + k] = __float2half_rn(sinf(e));
         r[3 + 24 + d * 8 + k] = __float2half_rn(cosf(e));
       }
@@ -587,7 +600,7 @@ __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const flo
     for (int k = 0; k < F; ++k) {
       float f = (float)(1 << k);
       if (include_pi) f = rnd_h(f * 3.14159265358979323846f);
-      const float e = rnd_h(xh[d] * f);  // fp16 product (frequencies buffer is cast to fp16 with the module)
+      const float e = kF32 ? xh[d] * f : rnd_h(xh[d] * f);  // fp16 product (frequencies buffer is cast to fp16 with the module)
       o[3 + d * F + k] = __float2half_rn(sinf(e));
       o[3 + 3 * F + d * F + k] = __float2half_rn(cosf(e));
     }
@@ -884,6 +897,17 @@ extern "C" int r3g_points_fourier(r3g_ctx* ctx, const void* queries, void* out, 
   if (n <= 0) return R3G_OK;
   points_fourier_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)queries, (__half*)out, out_ld, n, num_freqs, include_pi);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_points_fourier_f32(r3g_ctx* ctx, const float* queries, void* out, int64_t out_ld, int64_t n,
+                                      int num_freqs, int include_pi, void* stream) {
+  R3G_NEED_GPU(ctx, "points_fourier_f32");
+  if (!queries || !out || out_ld < 3 + 6 * num_freqs) return r3g_fail(ctx, R3G_E_INVALID, "points_fourier_f32: bad arguments");
+  if (n <= 0) return R3G_OK;
+  points_fourier_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(queries, (__half*)out, out_ld, n,
+                                                                                             num_freqs, include_pi);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

@@ -71,6 +71,7 @@ SIGNATURES = {
     "r3g_cfg_euler_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _vp]),
     "r3g_grid_fourier": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i, _i, _vp]),
     "r3g_points_fourier": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
+    "r3g_points_fourier_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
     "r3g_lnpost_dot": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "r3g_unproject": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }

@@ -313,6 +313,17 @@ def points_fourier(queries, out, num_freqs, include_pi):
     return out
 
 
+def points_fourier_f32(queries, out, num_freqs, include_pi):
+    """Fourier features of explicit FLOAT32 query points [n, 3] (float32 arithmetic, fp16 result; FlashVDM levels)."""
+    if queries.dtype != torch.float32:
+        raise TypeError("queries must be float32")
+    ctx = _ctx(queries)
+    q = queries.contiguous()
+    ctx.check(ctx.lib.r3g_points_fourier_f32(ctx.handle, _p(q), _p(out), out.stride(0), q.shape[0], int(num_freqs),
+                                             int(include_pi), _stream()))
+    return out
+
+
 def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
     ctx = _ctx(x)
     x2, rows, width, ldx, _, _ = _rows(x, "x")

@@ -211,8 +211,11 @@ class Hunyuan3DDiTPipeline:
     def compile(self):
         return None  # the reference torch.compile()s three modules; here the kernels are already native
 
-    def enable_flashvdm(self, *args, **kwargs):
-        self.vae.enable_flashvdm_decoder(True)
+    def enable_flashvdm(self, enabled=True, adaptive_kv_selection=True, topk_mode="mean", mc_algo="mc", replace_vae=True):
+        """pipelines.py:258-290.  The reference also swaps in the `-turbo` VAE checkpoint when `replace_vae` and the
+        model path is a known one; with no checkpoints reachable here the loaded VAE is kept."""
+        self.vae.enable_flashvdm_decoder(enabled=enabled, adaptive_kv_selection=adaptive_kv_selection,
+                                         topk_mode=topk_mode, mc_algo=mc_algo)
 
     def disable_flashvdm(self):
         self.vae.enable_flashvdm_decoder(False)

@@ -105,6 +105,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Threads for the CPU arm: the physical cores.  torchrun exports OMP_NUM_THREADS=1 for nproc > 1 (round 1's arm
+    slowed 9x exactly at N = 2), and one thread per LOGICAL core measured 4x slower than per physical core here
+    (128 vs 64 on the r2b box: 8.5e-5 vs 3.5e-4 objects/s)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        n = None
+    return int(n or max(1, (os.cpu_count() or 2) // 2))
+
+
 def synthetic_crop(seed, size=512):
     """512x512 RGBA: uniform-noise RGB inside an elliptical alpha mask."""
     import numpy as np
@@ -135,7 +147,7 @@ def reference_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline
     vals, det = [], None
@@ -384,7 +396,7 @@ def main_shapegen(args):
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import cpu_baseline
-            torch.set_num_threads(os.cpu_count() or 1)
+            torch.set_num_threads(host_threads())
             v, det = cpu_baseline.time_object_sample(R, args.dit_steps)
             line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": det["sample"], "sampled_cpu_seconds": det["sampled_cpu_seconds"],
@@ -514,7 +526,7 @@ def main_vggt(args):
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import cpu_baseline
-            torch.set_num_threads(os.cpu_count() or 1)
+            torch.set_num_threads(host_threads())
             v, det = cpu_baseline.time_vggt_sample(S, reps=3)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": det["sample"], "sampled_cpu_seconds": det["sampled_cpu_seconds"]}

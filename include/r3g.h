@@ -194,6 +194,11 @@ int r3g_grid_fourier(r3g_ctx* ctx, void* out, int64_t out_ld, int64_t start, int
  * CrossAttentionDecoder.forward, attention_blocks.py:484-486). */
 int r3g_points_fourier(r3g_ctx* ctx, const void* queries, void* out, int64_t out_ld, int64_t n, int num_freqs,
                        int include_pi, void* stream);
+/* The same for FLOAT32 query points [n,3]: FlashVDMVolumeDecoding builds its refinement-level queries in float32
+ * (volume_decoders.py:395-396) and CrossAttentionDecoder.forward embeds them before casting to the latents' dtype
+ * (attention_blocks.py:486), so x * f, sin and cos are float32 arithmetic and only the features are rounded to fp16. */
+int r3g_points_fourier_f32(r3g_ctx* ctx, const float* queries, void* out, int64_t out_ld, int64_t n, int num_freqs,
+                           int include_pi, void* stream);
 /* logits[r] = float(fp16( LN(x[r,:]; w,b,eps) . w_out + b_out ))  -- ln_post + output_proj
  * (attention_blocks.py:491-493), written to the float32 grid at out[r]. */
 int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width, float eps, const void* ln_w,

@@ -119,6 +119,51 @@ def golden_vae():
     print("vae_mini: grid", tuple(grid.shape), "range", float(grid.min()), float(grid.max()))
 
 
+def golden_flashvdm():
+    """FlashVDMVolumeDecoding (volume_decoders.py:280-435) with FlashVDMCrossAttentionProcessor (attention_processors.py:
+    35-79) on a mini geo-decoder, two levels (31 -> 62): the reference CLASS is run in fp32.  Its level-0 queries are
+    `xyz.to(dtype)`; the fp16 pipeline therefore sees fp16-quantised coordinates there, so generate_dense_grid_points is
+    wrapped to hand the class fp16-representable float32 coordinates (levels >= 1 build float32 queries in both)."""
+    ab, ap, vd = ref_import.hunyuan_autoencoders()
+    width, heads, n_lat = 128, 2, 48
+    torch.manual_seed(4)
+    fe = ab.FourierEmbedder(num_freqs=8, include_pi=False)
+    geo = ab.CrossAttentionDecoder(fourier_embedder=fe, out_channels=1, num_latents=n_lat, mlp_expand_ratio=4,
+                                   downsample_ratio=1, enable_ln_post=True, width=width, heads=heads,
+                                   qkv_bias=False, qk_norm=True, label_type="binary")
+    with torch.no_grad():
+        for n, p in geo.named_parameters():
+            if "norm" in n or "ln_" in n:
+                p.copy_((1.0 if n.endswith("weight") else 0.0) + 0.2 * torch.randn_like(p))
+        geo.output_proj.weight.mul_(6.0)       # logits of a few units: the |logit| < 0.95 band is a fraction of the volume
+    geo.eval()
+    fp16_round_(geo)
+    lat = (torch.randn(1, n_lat, width) * 0.7).half().float()
+    orig = vd.generate_dense_grid_points
+
+    def fp16_points(*a, **kw):
+        xyz, gs, ln = orig(*a, **kw)
+        return xyz.astype(np.float16).astype(np.float32), gs, ln
+    vd.generate_dense_grid_points = fp16_points
+    try:
+        dec = vd.FlashVDMVolumeDecoding(topk_mode="mean")
+        with torch.no_grad():
+            grid = dec(lat, geo, bounds=1.01, num_chunks=3000, mc_level=0.0, octree_resolution=64, min_resolution=31,
+                       mini_grid_num=4, enable_pbar=False)
+            grid0 = dec(lat, geo, bounds=1.01, num_chunks=3000, mc_level=0.0, octree_resolution=31, min_resolution=31,
+                        mini_grid_num=4, enable_pbar=False)
+    finally:
+        vd.generate_dense_grid_points = orig
+    d = sd_np(geo, "geo_decoder.")
+    d = {k: v for k, v in d.items() if "fourier_embedder" not in k}
+    g = grid.numpy()
+    d.update(latents=lat.numpy(), grid=g, grid_level0=grid0.numpy(), cfg_heads=np.int64(heads),
+             cfg_octree=np.int64(64), cfg_min_resolution=np.int64(31), cfg_num_chunks=np.int64(3000))
+    np.savez_compressed(os.path.join(OUT, "flashvdm_mini.npz"), **d)
+    print("flashvdm_mini: grid", g.shape, "finite", float(np.isfinite(g).mean()), "range", float(np.nanmin(g)),
+          float(np.nanmax(g)), "level0", grid0.shape)
+
+
 def golden_scheduler():
     s = ref_import.hunyuan_scheduler()
     sch = s.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000)
@@ -227,6 +272,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_dit()
     golden_vae()
+    golden_flashvdm()
     golden_scheduler()
     golden_unproject()
     golden_vggt()

@@ -122,3 +122,33 @@ def test_conditioner_mirror_against_reference_when_available():
         assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), (a - b).abs().max()
     u = SingleImageEncoder(mine).unconditional_embedding(2)["main"]
     assert u.shape == (2, 17, 32) and not u.any() and torch.equal(u, theirs.unconditional_embedding(2))
+
+
+def test_near_surface_mask_against_reference_when_available():
+    """extract_near_surface_volume_fn (volume_decoders.py:29-119): the point selection of the FlashVDM levels."""
+    import ref_import
+    if not ref_import.available():
+        pytest.skip("/root/reference not present")
+    import warnings
+    _, _, vd = ref_import.hunyuan_autoencoders()
+    from r3g.vae import extract_near_surface_volume_fn
+    torch.manual_seed(0)
+    for n in (5, 9):
+        x = torch.randn(n, n, n)
+        x[torch.rand(n, n, n) < 0.25] = -10000.0
+        for alpha in (0.0, 0.3, -0.2):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = vd.extract_near_surface_volume_fn(x, alpha)
+            assert torch.equal(extract_near_surface_volume_fn(x, alpha), want)
+
+
+def test_flashvdm_resolution_schedule():
+    """volume_decoders.py:310-320: 256 -> [63, 126, 252]; below min_resolution a single level."""
+    from r3g.vae import FlashVDMVolumeDecoding
+    dec = FlashVDMVolumeDecoding()
+    with pytest.raises(ValueError):
+        FlashVDMVolumeDecoding("nope")
+    with pytest.raises(NotImplementedError):
+        FlashVDMVolumeDecoding("merge")
+    assert dec._topk(3072) == 1024 and dec._topk(512) == 256 and dec._topk(48) == 16
