@@ -607,6 +607,29 @@ __device__ __forceinline__ void fourier_row(__half* o, int64_t out_ld, const flo
   for (int c = 3 + 6 * F; c < out_ld; ++c) o[c] = __float2half_rn(0.f);
 }
 
+// ------------------------------------------------------------------------------------------- SwiGLU gate
+// out[r, j] = fp16( fp16(silu(x[r, j])) * x[r, F + j] ): Dinov2SwiGLUFFN (transformers modeling_dinov2.py: hidden =
+// silu(x1) * x2 after weights_in(...).chunk(2)), the MLP of the DINOv2-giant conditioner (conditioner.py:125-131).
+__global__ void __launch_bounds__(256) swiglu_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ out,
+                                                     int64_t ldo, int64_t rows, int F) {
+  pdl_wait();
+  pdl_trigger();
+  const int chunks = F >> 3;
+  const int64_t total = rows * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c = (int)(i - r * chunks);
+    const Half8 a = *reinterpret_cast<const Half8*>(x + r * ldx + 8 * c);
+    const Half8 b = *reinterpret_cast<const Half8*>(x + r * ldx + F + 8 * c);
+    float fa[8], fb[8], o[8];
+    unpack8(a, fa);
+    unpack8(b, fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = rnd_h(fa[k] / (1.f + __expf(-fa[k]))) * fb[k];
+    *reinterpret_cast<Half8*>(out + r * ldo + 8 * c) = pack8(o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- ln_post + output_proj
 template <int NCH>
 __global__ void __launch_bounds__(256, NCH == 4 ? 3 : 2) lnpost_dot_kernel(const __half* __restrict__ x, int64_t ldx, int rows,
@@ -897,6 +920,20 @@ extern "C" int r3g_points_fourier(r3g_ctx* ctx, const void* queries, void* out, 
   if (n <= 0) return R3G_OK;
   points_fourier_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)queries, (__half*)out, out_ld, n, num_freqs, include_pi);
+  R3G_LAUNCH_OK(ctx);
+  return R3G_OK;
+}
+
+extern "C" int r3g_swiglu(r3g_ctx* ctx, const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int F,
+                          void* stream) {
+  R3G_NEED_GPU(ctx, "swiglu");
+  if (!x || !out || F < 8 || F % 8 || ldx % 8 || ldo % 8 || ldx < 2 * (int64_t)F || ldo < F || !aligned16(x) || !aligned16(out))
+    return r3g_fail(ctx, R3G_E_INVALID, "swiglu: F %% 8 == 0, ldx >= 2F, 16-byte aligned rows required");
+  if (rows <= 0) return R3G_OK;
+  const int64_t total = rows * (F / 8);
+  const unsigned grid = (unsigned)min((total + 255) / 256, (int64_t)ctx->num_sms * 8);
+  R3G_CUDA_OK(ctx, r3g_launch_pdl(ctx, swiglu_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, ldx,
+                                   (__half*)out, ldo, rows, F));
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }

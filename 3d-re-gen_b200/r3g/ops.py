@@ -273,6 +273,20 @@ def gemv(w, bias, vec, silu_in=False, silu_out=False, out=None):
     return out
 
 
+def swiglu(x, F, out=None):
+    """out[:, j] = silu(x[:, j]) * x[:, F + j]  (fp16 roundings of Dinov2SwiGLUFFN); x [M, 2F] -> out [M, F]."""
+    _f16(x, "x")
+    ctx = _ctx(x)
+    x2, rows, width, ldx, _, _ = _rows(x, "x")
+    if width < 2 * F:
+        raise ValueError("swiglu: x must hold 2F columns")
+    if out is None:
+        out = torch.empty(*x.shape[:-1], F, device=x.device, dtype=torch.float16)
+    o2, orow, _, ldo, _, _ = _rows(out, "out")
+    ctx.check(ctx.lib.r3g_swiglu(ctx.handle, _p(x2), ldx, _p(o2), ldo, rows, int(F), _stream()))
+    return out
+
+
 def timestep_embedding(t, dim=256, time_factor=1000.0, max_period=10000.0, out=None):
     _f16(t, "t")
     ctx = _ctx(t)

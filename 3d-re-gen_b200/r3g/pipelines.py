@@ -185,6 +185,7 @@ class Hunyuan3DDiTPipeline:
             if bad:
                 raise RuntimeError(f"unexpected conditioner keys (not under {pre!r}): {bad[:5]}")
             enc.model.load_state_dict({k[len(pre):]: v for k, v in ckpt["conditioner"].items()}, strict=True)
+            enc.invalidate()
         return cls(vae=vae, model=model, scheduler=FlowMatchEulerDiscreteScheduler(**config["scheduler"]["params"]),
                    conditioner=SingleImageEncoder(enc),
                    image_processor=ImageProcessorV2(**config["image_processor"]["params"]), device=device,

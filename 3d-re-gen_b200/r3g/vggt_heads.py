@@ -185,18 +185,20 @@ class DPTHead:
 class VGGT:
     """`model.aggregator / model.camera_head / model.depth_head`, as the stage script uses the reference's VGGT."""
 
-    def __init__(self, img_size=518, patch_size=14, embed_dim=1024, device="cuda", **agg_kwargs):
+    def __init__(self, img_size=518, patch_size=14, embed_dim=1024, device="cuda", camera_head_kwargs=None,
+                 depth_head_kwargs=None, **agg_kwargs):
         from .vggt import Aggregator
         self.device = torch.device(device)
         self.aggregator = Aggregator(img_size=img_size, patch_size=patch_size, embed_dim=embed_dim, device=device,
                                      **agg_kwargs)
         self.camera_head = self.depth_head = None
         self.patch_size = patch_size
+        self._ck, self._dk = dict(camera_head_kwargs or {}), dict(depth_head_kwargs or {})
 
     def load_state_dict(self, sd, strict=True):
         self.aggregator.load_state_dict(sd, prefix="aggregator.")
-        self.camera_head = CameraHead(sd, device=self.device)
-        self.depth_head = DPTHead(sd, patch_size=self.patch_size, device=self.device)
+        self.camera_head = CameraHead(sd, device=self.device, **self._ck)
+        self.depth_head = DPTHead(sd, patch_size=self.patch_size, device=self.device, **self._dk)
         return self
 
     def eval(self):

@@ -170,6 +170,10 @@ int r3g_qk_norm(r3g_ctx* ctx, void* buf, int64_t ld, int rows, int heads, int64_
  * MLPEmbedder hunyuan3ddit.py:79-80, LastLayer.adaLN_modulation :275).  fp16 in/out, fp32 accumulate. */
 int r3g_gemv(r3g_ctx* ctx, const void* w, const void* bias, const void* vec, int64_t vec_ld, void* out,
              int64_t out_ld, int B, int N, int K, int silu_in, int silu_out, void* stream);
+/* SwiGLU gate of the DINOv2-giant conditioner's MLP (Hunyuan3D-2/hy3dgen/shapegen/models/conditioner.py:125-131 runs
+ * transformers' Dinov2Model; its Dinov2SwiGLUFFN computes weights_out(silu(x1) * x2) with x1, x2 = weights_in(h).chunk(2)):
+ * out[r, j] = fp16(fp16(silu(x[r, j])) * x[r, F + j]) for j < F; x fp16 [rows, >= 2F] (ldx), out fp16 [rows, >= F] (ldo). */
+int r3g_swiglu(r3g_ctx* ctx, const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int F, void* stream);
 /* timestep_embedding(t, 256, time_factor=1000): cat(cos, sin), fp16 out [B,256] (hunyuan3ddit.py:39-60). */
 int r3g_timestep_embedding(r3g_ctx* ctx, const void* t_f16, void* out, int B, int dim, float time_factor,
                            float max_period, void* stream);

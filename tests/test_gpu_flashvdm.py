@@ -91,11 +91,12 @@ def test_flashvdm_full_width_evaluates_a_fraction_of_the_grid():
     e1.record()
     torch.cuda.synchronize()
     assert dec.stats["resolutions"] == [63, 126, 252] and grid.shape == (1, 253, 253, 253)
+    per_level = list(dec.stats["queries"])
     dense = vae.volume_decoder(lat, vae.geo_decoder, bounds=1.01, octree_resolution=63)
     lvl0 = dec(lat, vae.geo_decoder, bounds=1.01, octree_resolution=63, enable_pbar=False)
     scale = dense.abs().max().item()
     conf = dense.abs() > 5e-2 * scale
     agree = (torch.sign(lvl0.float()[conf]) == torch.sign(dense[conf])).float().mean().item()
-    print(f"FlashVDM 252^3: {e0.elapsed_time(e1):.0f} ms, queries per level {dec.stats['queries']} of {253 ** 3}; "
+    print(f"FlashVDM 252^3: {e0.elapsed_time(e1):.0f} ms, queries per level {per_level} of {253 ** 3} (a noise-like field of random weights keeps most of the volume inside the |logit| < 0.95 band); "
           f"top-1024-of-3072 attention vs full attention at 64^3: sign agreement {agree:.4f} on confident points")
     assert agree > 0.9

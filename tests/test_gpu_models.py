@@ -120,3 +120,33 @@ def test_vae_full_width_layer_against_oracle():
     sd = {k: v.float().cuda() for k, v in vae.reference_state_dict().items()}
     ref = R.vae_forward(sd, zl.float(), 16, 2)
     assert rel_l2(out, ref) < 3e-3
+
+
+def test_conditioner_on_r3g_kernels_against_the_hf_module():
+    """rows a2 / f4: the DINOv2 forward of the conditioner on the r3g kernels vs transformers' Dinov2Model (the module
+    the reference runs, conditioner.py:125-131) in fp32 on the same weights; incl. a SwiGLU width that needs padding."""
+    from r3g.conditioner import DinoImageEncoder
+    for hidden, heads, mlp in ((192, 3, 4), (128, 2, 4)):          # SwiGLU widths 512 and 344 (padded to 352)
+        cfg = dict(hidden_size=hidden, num_hidden_layers=3, num_attention_heads=heads, mlp_ratio=mlp, patch_size=14,
+                   image_size=70, use_swiglu_ffn=True, layerscale_value=1.0, qkv_bias=True, hidden_act="gelu",
+                   layer_norm_eps=1e-6)
+        torch.manual_seed(0)
+        enc = DinoImageEncoder(config=cfg, image_size=70, device="cuda", dtype=torch.float16)
+        assert enc.backend == "r3g"
+        with torch.no_grad():
+            for n, p_ in enc.model.named_parameters():
+                if "lambda1" in n:
+                    p_.copy_(0.3 + 0.2 * torch.rand_like(p_))
+                elif "norm" in n and n.endswith("weight"):
+                    p_.copy_(1 + 0.2 * torch.randn_like(p_))
+        img = torch.rand(2, 3, 90, 90) * 2 - 1
+        got = enc(img)
+        ref_model = type(enc.model)(enc.model.config).to("cuda").float()
+        ref_model.load_state_dict({k: v.float() for k, v in enc.model.state_dict().items()})
+        with torch.no_grad():
+            px = enc._transform(((img + 1) / 2).cuda().half()).float()
+            ref = ref_model(px).last_hidden_state
+        assert got.shape == ref.shape == (2, 26, hidden) and got.dtype == torch.float16
+        assert rel_l2(got, ref) < 5e-3, rel_l2(got, ref)
+        enc.backend = "hf"
+        assert rel_l2(enc(img), ref) < 5e-3

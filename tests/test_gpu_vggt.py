@@ -84,3 +84,42 @@ def test_aggregator_full_width_against_oracle():
     ref = V.aggregator({k: v.cuda() for k, v in sd.items()}, imgs, depth, 16)
     for o, r in zip(outs, ref):
         assert rel_l2(o, r) < 5e-3
+
+
+def test_run_vggt_composite_against_cpu_oracle():
+    """row v2: aggregator (r3g kernels) -> camera head -> pose_encoding_to_extri_intri -> DPT depth head ->
+    r3g_unproject, strung together by the stage twin's run_VGGT, against the fp32 CPU path: oracle aggregator, the same
+    head mirrors on the CPU (pinned against the reference modules in tests/test_oracle_golden.py) and the oracle's
+    numpy back-projection."""
+    import importlib.util
+    import hy3d_ref as R
+    import vggt_ref as V
+    from r3g import ops
+    from r3g.vggt_heads import CameraHead, DPTHead, VGGT, pose_encoding_to_extri_intri, random_state_dict
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("stage4", os.path.join(root, "stages", "camera_and_pointcloud",
+                                                                          "minimal_demo_vggt.py"))
+    stage4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stage4)
+    C, depth = 128, 2
+    sd = random_state_dict(3, embed_dim=C, depth=depth, vit_depth=2, trunk_depth=2, features=32,
+                           out_channels=(32, 64, 128, 128), img_size=56)
+    sd = {k: v.half().float() for k, v in sd.items()}
+    hk, dk = dict(trunk_depth=2, num_heads=4), dict(intermediate_layer_idx=(0, 1, 0, 1))
+    model = VGGT(img_size=56, embed_dim=C, depth=depth, num_heads=2, vit_depth=2, patch_embed="dinov2_vits14_reg",
+                 camera_head_kwargs=hk, depth_head_kwargs=dk).load_state_dict(sd)
+    torch.manual_seed(0)
+    images = torch.rand(2, 3, 112, 112)
+    E, K, dmap, conf = stage4.run_VGGT(model, images.cuda(), resolution=56)
+    pts = ops.unproject(dmap[..., 0].contiguous(), E, K, torch.float64).cpu().numpy()
+    # CPU fp32 path
+    im = torch.nn.functional.interpolate(images, size=(56, 56), mode="bilinear", align_corners=False)[None]
+    asd = {k[len("aggregator."):]: v for k, v in sd.items() if k.startswith("aggregator.")}
+    toks = V.aggregator(asd, im, depth, 2, vit_depth=2)
+    pose = CameraHead(sd, device="cpu", **hk)(toks)[-1]
+    Er, Kr = pose_encoding_to_extri_intri(pose, im.shape[-2:])
+    dr, cr = DPTHead(sd, device="cpu", **dk)(toks, im, 5)
+    assert np.abs(E - Er[0].numpy()).max() < 5e-3 and np.abs(K - Kr[0].numpy()).max() < 5e-2 * np.abs(Kr[0].numpy()).max()
+    assert rel_l2(dmap, dr[0]) < 1e-2 and rel_l2(conf, cr[0]) < 1e-2
+    ref_pts = R.unproject_depth_map_to_point_map(dmap.cpu().numpy(), E, K)
+    assert pts.dtype == np.float64 and np.array_equal(pts, ref_pts)      # the back-projection itself is exact
