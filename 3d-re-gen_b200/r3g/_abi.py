@@ -59,6 +59,7 @@ SIGNATURES = {
     "r3g_mc_count": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _sz, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "r3g_mc_extract": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _sz, _vp, _vp, _vp]),
     "r3g_mc_classify": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "r3g_mesh_components": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "r3g_linear": (_i, [_vp, C.POINTER(LinearArgs), _vp]),
     "r3g_attention": (_i, [_vp, C.POINTER(AttentionArgs), _vp]),
     "r3g_layernorm": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _vp]),

@@ -436,6 +436,17 @@ def marching_cubes(grid, level=0.0, bounds=None):
     return verts, faces
 
 
+def mesh_components(faces, num_vertices):
+    """labels int32 [num_vertices]: the smallest vertex index of each vertex's connected component (see r3g.h)."""
+    if faces.dtype != torch.int32 or faces.dim() != 2 or faces.shape[1] != 3:
+        raise TypeError("faces must be int32 [F, 3]")
+    ctx = _ctx(faces)
+    f = faces.contiguous()
+    labels = torch.empty(int(num_vertices), device=faces.device, dtype=torch.int32)
+    ctx.check(ctx.lib.r3g_mesh_components(ctx.handle, _p(f), f.shape[0], int(num_vertices), _p(labels), _stream()))
+    return labels
+
+
 def mc_classify(grid, level=0.0):
     grid = grid.contiguous()
     ctx = _ctx(grid)

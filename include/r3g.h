@@ -64,6 +64,13 @@ int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, floa
 int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level,
                     unsigned char* case_out, void* stream);
 
+/* Connected components of a triangle mesh (vertices joined by the faces): labels[v] = the smallest vertex index of v's
+ * component.  The computation behind FloaterRemover (Hunyuan3D-2/hy3dgen/shapegen/postprocessors.py:58-63,118-129:
+ * pymeshlab "select small disconnected components" with nbfaceratio 0.005 + delete), applied to every generated mesh
+ * by src/2d_to_3d_models/run.py:93.  faces int32 [nf][3] with indices in [0, nv); labels int32 [nv].
+ * SYNCHRONISES `stream` (it reports an out-of-range index as R3G_E_INVALID). */
+int r3g_mesh_components(r3g_ctx* ctx, const int32_t* faces, int64_t nf, int64_t nv, int32_t* labels, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense-contraction building blocks (tcgen05 / TMEM / TMA).  Used by the DiT, ShapeVAE and geo-decoder
  * mirrors; exported so that tests can check each against the oracle in isolation.

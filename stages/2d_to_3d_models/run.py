@@ -10,8 +10,10 @@ Differences, all on purpose:
   * one process per GPU (torchrun / torch.distributed, NCCL) instead of a spawn-pool that reloads both models for
     every image (reference run.py:108-133): each rank loads the weights once, takes images i % world == rank of
     the SORTED list, and the finished meshes are gathered to rank 0 over NCCL, which writes every .glb;
-  * shape generation only: the mesh cleaners (pymeshlab) and the texture pipeline are outside the hot path
-    (SURVEY.md section 8f rows 2 and 4) -- the .glb holds the untextured shape;
+  * FloaterRemover runs on the GPU (r3g/postprocessors.py: union-find components, MeshLab's 0.5 % rule) and
+    DegenerateFaceRemover is the reference's no-op round trip; FaceReducer (pymeshlab quadric decimation to 40 000 faces)
+    and the texture pipeline are not mirrored -- the .glb holds the cleaned,
+    undecimated, untextured shape;
   * `--random-weights` builds the Hunyuan3D-2 architecture with seeded random weights when no checkpoint is
     reachable (this build environment has no network).
 
@@ -34,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "3d-re-gen_b200"))
 
 from r3g.dist import gather_meshes, shard_indices  # noqa: E402
 from r3g.pipelines import Hunyuan3DDiTFlowMatchingPipeline, SimpleMesh  # noqa: E402
+from r3g.postprocessors import DegenerateFaceRemover, FloaterRemover  # noqa: E402
 
 
 def load_config(path):
@@ -81,7 +84,7 @@ def main():
         repo = "tencent/Hunyuan3D-2mini" if mini else "tencent/Hunyuan3D-2"
         kw = dict(subfolder="hunyuan3d-dit-v2-mini", variant="fp16") if mini else {}
         pipe = Hunyuan3DDiTFlowMatchingPipeline.from_pretrained(repo, device=f"cuda:{local}", **kw)
-    pipe.vae.surface_extractor.keep_on_device = world > 1
+    pipe.vae.surface_extractor.keep_on_device = True     # the mesh leaves the GPU once, after the floater removal
 
     mine = shard_indices(len(names), rank, world)
     local_meshes, local_names = [], []
@@ -99,6 +102,10 @@ def main():
         v, f = out.mesh_v, out.mesh_f
         if not torch.is_tensor(v):
             v, f = torch.from_numpy(v), torch.from_numpy(f)
+        # src/2d_to_3d_models/run.py:93-94 (FaceReducer, :95, is not mirrored)
+        v, f = DegenerateFaceRemover()(FloaterRemover()((v, f), device=f"cuda:{local}"))
+        if world == 1:
+            v, f = v.cpu(), f.cpu()
         local_meshes.append((v, f))
         local_names.append(stem)
         print(f"[rank {rank}] {stem}: {v.shape[0]} vertices, {f.shape[0]} faces in {time.time() - t0:.2f} s", flush=True)
