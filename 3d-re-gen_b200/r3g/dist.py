@@ -87,7 +87,7 @@ class MeshStreamGatherer:
     and without a host round trip; the messages move over NCCL on a SIDE stream (NVLink / NVSwitch; a few hundred MB
     per step) while the compute stream runs the next object.  On rank 0 the sizes are read one step later (by then the
     step's header copy has long landed: no stall), the payloads go device -> PINNED ring -> a consumer thread that
-    hands the arrays to `sink(step, rank, verts, faces)` (default: keep them for `finish()`).  Nothing on this path is
+    hands the arrays to `sink(step, rank, verts, faces)` (views into the ring slot; default: copies kept for `finish()`).  Nothing on this path is
     a pageable synchronous `.cpu()` (round 1's limiter: 4.8 GB/s into rank 0).
 
     Also runs on gloo with CPU tensors (tests/test_dist_gloo.py), where streams do not exist and every wait is a host
@@ -151,15 +151,15 @@ class MeshStreamGatherer:
                 if event is not None:
                     event.synchronize()
                 for r, (nv, nf) in enumerate(sizes):
-                    src = self.land[slot][r] if self.to_host else (self.send[slot] if r == 0 else self.recv[slot][r - 1])
-                    v = src[4:4 + 3 * nv].view(torch.float32).view(nv, 3).clone()
-                    f = src[4 + 3 * nv:4 + 3 * nv + 3 * nf].view(nf, 3).clone()
                     if nv == 0 and nf == 0:
                         continue
+                    src = self.land[slot][r] if self.to_host else (self.send[slot] if r == 0 else self.recv[slot][r - 1])
+                    v = src[4:4 + 3 * nv].view(torch.float32).view(nv, 3)      # views into the ring slot: a sink that
+                    f = src[4 + 3 * nv:4 + 3 * nv + 3 * nf].view(nf, 3)        # keeps them must copy before returning
                     if self.sink is not None:
                         self.sink(step, r, v, f)
                     else:
-                        self.results[(step, r)] = (v, f)
+                        self.results[(step, r)] = (v.clone(), f.clone())
                 self.slot_free[slot].set()
         except Exception as e:      # surfaced by finish()
             self.err = e
@@ -184,6 +184,9 @@ class MeshStreamGatherer:
             for r, (nv, nf) in enumerate(sizes):
                 n = 4 + 3 * nv + 3 * nf
                 self.land[slot][r][:n].copy_((self.send[slot] if r == 0 else self.recv[slot][r - 1])[:n])
+        elif self.cuda:          # device-resident consumer: it must still see the transfers of this step completed
+            event = torch.cuda.Event()
+            event.record(self.side)
         self.q.put((step, slot, event, sizes))
 
     # ------------------------------------------------------------------------------------------------ API

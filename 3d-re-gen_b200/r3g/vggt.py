@@ -135,6 +135,8 @@ class Aggregator:
         self.patch_start_idx = 1 + num_register_tokens
         self.device = torch.device(device)
         self._ws = {}
+        self.use_cuda_graph = True
+        self._graphs = {}
 
     def load_state_dict(self, sd, prefix=""):
         dev = self.device
@@ -172,7 +174,32 @@ class Aggregator:
 
     @torch.no_grad()
     def forward(self, images):
-        """images [B,S,3,H,W] float in [0,1] -> (list of `depth` tensors [B,S,P,2C] float32, patch_start_idx)."""
+        """images [B,S,3,H,W] float in [0,1] -> (list of `depth` tensors [B,S,P,2C] float32, patch_start_idx).
+        The ~600 launches of a forward (8 per block, 15-30 us each at 2 frames) are captured into a CUDA graph per input
+        shape and replayed: eager, the host cannot issue them as fast as the GPU runs them.  The returned tensors are the
+        graph's static outputs -- valid until the next call with the same shape (`use_cuda_graph = False`: fresh ones)."""
+        if not (self.use_cuda_graph and images.is_cuda):
+            return self._forward(images)
+        key = tuple(images.shape)
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(x=images.clone())
+            side = torch.cuda.Stream(images.device)
+            side.wait_stream(torch.cuda.current_stream(images.device))
+            with torch.cuda.stream(side):
+                self._forward(st["x"])                   # warm-up: workspaces, lazily set function attributes
+            torch.cuda.current_stream(images.device).wait_stream(side)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                st["out"] = self._forward(st["x"])
+            g = (cg, st)
+            self._graphs = {key: g}
+        cg, st = g
+        st["x"].copy_(images)
+        cg.replay()
+        return st["out"]
+
+    def _forward(self, images):
         B, S, C_in, H, W = images.shape
         if C_in != 3:
             raise ValueError(f"Expected 3 input channels, got {C_in}")
