@@ -252,6 +252,9 @@ def random_state_dict(seed=0, embed_dim=1024, depth=24, vit_depth=24, trunk_dept
     for n, shp in (("embed_pose", (D, 9)), ("poseLN_modulation.1", (3 * D, D)), ("pose_branch.fc1", (D // 2, D)),
                    ("pose_branch.fc2", (9, D // 2))):
         sd[c + n + ".weight"], sd[c + n + ".bias"] = rn(*shp), rn(shp[0])
+    # a usable camera out of random weights: unit-ish quaternion and a positive field of view (FoV = relu(.) of the last
+    # two pose entries; 0 would put the focal length at infinity)
+    sd[c + "pose_branch.fc2.bias"] = torch.tensor([0.1, -0.2, 0.3, 0.05, -0.05, 0.02, 1.0, 0.9, 0.8])
     for i in range(trunk_depth):
         block(f"{c}trunk.{i}.", D, False)
         sd[f"{c}trunk.{i}.ls1.gamma"], sd[f"{c}trunk.{i}.ls2.gamma"] = torch.full((D,), 0.01), torch.full((D,), 0.01)

@@ -192,8 +192,9 @@ def reference_arm(args):
 
 # DRAM traffic of the DiT forward's GEMM launches: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one
 # forward (tools/prof_dit_gemm.py), averaged per launch like `achieved`; the committed capture is named beside it.
-GEMM_TRAFFIC_NCU = {"source": "profiles/r2_ncu_dit_gemm_traffic.csv", "dram_bytes_per_launch": None,
-                    "algorithmic_bytes_per_launch": None}
+GEMM_TRAFFIC_NCU = {"source": "profiles/r2d_ncu_dit_gemm_traffic.csv.gz (131 launches of one forward, cold L2 per launch "
+                              "under ncu: an upper bound of the in-graph traffic)",
+                    "dram_bytes_per_launch": 85.34e6}
 
 
 def instrumented_linear_roofline(pipe, cond, peak_tflops):
