@@ -358,13 +358,17 @@ def closed_form_inverse_se3(se3):
     return inv
 
 
-def unproject(depth, extrinsic, intrinsic, out_dtype=torch.float64):
-    """depth: CUDA float32 [S,H,W]; extrinsic [S,3,4] / intrinsic [S,3,3]: host numpy float32 (cam from world)."""
+def unproject(depth, extrinsic, intrinsic, out_dtype=torch.float64, out=None):
+    """depth: CUDA float32 [S,H,W]; extrinsic [S,3,4] / intrinsic [S,3,3]: host numpy float32 (cam from world).
+    out: optional preallocated [S,H,W,3] tensor of `out_dtype` (a 1.6 GB float64 result is worth reusing)."""
     ctx = _ctx(depth)
     S, H, W = depth.shape
     c2w = np.ascontiguousarray(closed_form_inverse_se3(np.asarray(extrinsic))[:, :3, :].astype(np.float64))
     k = np.ascontiguousarray(np.asarray(intrinsic, dtype=np.float32).reshape(S, 9))
-    out = torch.empty(S, H, W, 3, device=depth.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty(S, H, W, 3, device=depth.device, dtype=out_dtype)
+    elif out.shape != (S, H, W, 3) or out.dtype != out_dtype or not out.is_contiguous():
+        raise ValueError("unproject: out must be a contiguous [S,H,W,3] tensor of out_dtype")
     ctx.check(ctx.lib.r3g_unproject(ctx.handle, _p(depth.contiguous()), c2w.ctypes.data_as(C.c_void_p),
                                     k.ctypes.data_as(C.c_void_p), _p(out), S, H, W,
                                     1 if out_dtype == torch.float64 else 0, _stream()))

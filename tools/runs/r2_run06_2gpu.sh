@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 O=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 300 python -m pytest tests/test_gpu_postprocess.py tests/test_gpu_vggt.py -q -m gpu --timeout 200 > $O/r2_06_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r2_06_pytest.log
 timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 > $O/r2_06_bench_2gpu.json 2> $O/r2_06_bench_2gpu.err; echo "bench2 rc=$?"; python -c "
 import json; d=json.loads(open('$O/r2_06_bench_2gpu.json').read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e'], d['clocks'])"; tail -5 $O/r2_06_bench_2gpu.err
 # stage-3 twin, 2 ranks, 5 crops (one skipped), few steps / small grid
