@@ -8,18 +8,19 @@
 namespace {
 
 // find with path halving; concurrent writers only ever replace a parent by one of its ancestors
-__device__ __forceinline__ int uf_find(int* __restrict__ parent, int x) {
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+  volatile int* vp = parent;     // L1 is not coherent across SMs: hooks (CAS at L2) must be seen by the retry loops
   while (true) {
-    const int p = parent[x];
+    const int p = vp[x];
     if (p == x) return x;
-    const int g = parent[p];
-    if (g != p) parent[x] = g;
+    const int g = vp[p];
+    if (g != p) vp[x] = g;
     x = p;
   }
 }
 
 // the larger root is hooked under the smaller one, so a component's final root is its smallest vertex index
-__device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b) {
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   while (true) {
     a = uf_find(parent, a);
     b = uf_find(parent, b);
@@ -34,7 +35,7 @@ __global__ void uf_init_kernel(int* __restrict__ parent, int64_t nv) {
   if (i < nv) parent[i] = (int)i;
 }
 
-__global__ void uf_hook_kernel(int* __restrict__ parent, const int32_t* __restrict__ faces, int64_t nf, int64_t nv,
+__global__ void uf_hook_kernel(int* parent, const int32_t* __restrict__ faces, int64_t nf, int64_t nv,
                                int* __restrict__ bad) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
@@ -47,9 +48,19 @@ __global__ void uf_hook_kernel(int* __restrict__ parent, const int32_t* __restri
   uf_union(parent, b, c);
 }
 
-__global__ void uf_flatten_kernel(int* __restrict__ parent, int32_t* __restrict__ label, int64_t nv) {
+// labels alias the parent array: the only writes in this pass are label[i] = root(i), each a valid (and final) parent of
+// i.  The walk must NOT compress here -- a halving store from a thread passing through i could land after i's own final
+// store and leave a non-root ancestor in label[i].
+__global__ void uf_flatten_kernel(int* parent, int64_t nv) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nv) label[i] = uf_find(parent, (int)i);
+  if (i >= nv) return;
+  int x = (int)i;
+  while (true) {
+    const int p = *reinterpret_cast<volatile int*>(parent + x);
+    if (p == x) break;
+    x = p;
+  }
+  parent[i] = x;
 }
 
 }  // namespace
@@ -74,7 +85,7 @@ extern "C" int r3g_mesh_components(r3g_ctx* ctx, const int32_t* faces, int64_t n
     uf_hook_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(parent, faces, nf, nv, bad_dev);
     R3G_LAUNCH_OK(ctx);
   }
-  uf_flatten_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(parent, labels, nv);
+  uf_flatten_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(parent, nv);
   R3G_LAUNCH_OK(ctx);
   int* bad_host = reinterpret_cast<int*>(ctx->pinned);
   R3G_CUDA_OK(ctx, cudaMemcpyAsync(bad_host, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, s));

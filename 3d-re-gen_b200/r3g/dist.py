@@ -103,6 +103,12 @@ class MeshStreamGatherer:
         self.device = torch.device(device) if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu"))
         self.cap_v, self.cap_f = int(cap_vertices), int(cap_faces)
+        if self.world > 1:
+            # every rank must post the SAME message size (an NCCL send / recv pair with different counts is undefined);
+            # callers size the capacity from their own meshes, so agree on the maximum
+            caps = torch.tensor([self.cap_v, self.cap_f], dtype=torch.int64, device=self.device)
+            dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+            self.cap_v, self.cap_f = int(caps[0]), int(caps[1])
         self.cap = 4 + 3 * self.cap_v + 3 * self.cap_f
         self.depth, self.to_host, self.step = depth, to_host, 0
         self.side = torch.cuda.Stream(self.device) if self.cuda else None

@@ -346,6 +346,55 @@ def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
     return out
 
 
+def _f32(t, name):
+    if t is not None and (t.dtype != torch.float32 or t.stride(-1) != 1):
+        raise TypeError(f"{name} must be float32 with unit inner stride")
+    return t
+
+
+def gemv_f32(w16, bias, vec, out=None, residual=None, gamma=None, silu_in=False, gelu_out=False):
+    """out[b] = residual[b] + gamma * g(W . a(vec[b]) + bias): fp16 weights, float32 everything else (see r3g.h)."""
+    _f16(w16, "w")
+    for t, n in ((bias, "bias"), (vec, "vec"), (residual, "residual"), (gamma, "gamma")):
+        _f32(t, n)
+    ctx = _ctx(vec)
+    B, K = vec.shape
+    N = w16.shape[0]
+    if out is None:
+        out = torch.empty(B, N, device=vec.device, dtype=torch.float32)
+    if residual is not None and residual.stride(0) != out.stride(0):
+        raise ValueError("gemv_f32: residual must share out's row stride")
+    ctx.check(ctx.lib.r3g_gemv_f32(ctx.handle, _p(w16), _p(bias), _p(vec), vec.stride(0), _p(out), out.stride(0),
+                                   _p(residual), _p(gamma), B, N, K, int(silu_in), int(gelu_out), _stream()))
+    return out
+
+
+def layernorm_f32(x, weight=None, bias=None, eps=1e-5, shift=None, scale=None, gate=None, out=None):
+    """float32 LayerNorm over the last dim of [rows, width]; with shift / scale / gate: gate * (LN(x)(1+scale)+shift) + x."""
+    _f32(x, "x")
+    ctx = _ctx(x)
+    rows, width = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    mod_ld = scale.stride(0) if scale is not None else 0
+    ctx.check(ctx.lib.r3g_layernorm_f32(ctx.handle, _p(x), x.stride(0), _p(out), out.stride(0), rows, width, float(eps),
+                                        _p(_f32(weight, "weight")), _p(_f32(bias, "bias")), _p(_f32(shift, "shift")),
+                                        _p(_f32(scale, "scale")), _p(_f32(gate, "gate")), mod_ld, _stream()))
+    return out
+
+
+def small_attention_f32(qkv, B, S, H, D, out=None):
+    """qkv float32 [B*S, 3*H*D] laid out (3, H, D) -> [B*S, H*D]; softmax over the S tokens of each batch element."""
+    _f32(qkv, "qkv")
+    ctx = _ctx(qkv)
+    if not qkv.is_contiguous() or qkv.shape != (B * S, 3 * H * D):
+        raise ValueError("small_attention_f32: qkv must be contiguous [B*S, 3*H*D]")
+    if out is None:
+        out = torch.empty(B * S, H * D, device=qkv.device, dtype=torch.float32)
+    ctx.check(ctx.lib.r3g_small_attention_f32(ctx.handle, _p(qkv), _p(out), B, S, H, D, float(D) ** -0.5, _stream()))
+    return out
+
+
 def closed_form_inverse_se3(se3):
     """numpy branch of vggt/vggt/utils/geometry.py:120-169: [R t]^-1 = [R^T, -R^T t], written into np.eye(4)
     (so the result is float64 holding float32-computed entries)."""

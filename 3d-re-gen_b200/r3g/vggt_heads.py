@@ -85,6 +85,78 @@ class CameraHead:
         return outs
 
 
+class CameraHeadR3G:
+    """The same head on libr3g.so (heads.cu): the trunk sees S tokens, so its 16 linears per iteration are GEMVs over
+    216 M parameters -- HBM-bound.  Weights fp16 (half the bytes), activations / residual stream / LayerNorm float32 as
+    in the reference (it runs the head outside autocast).  The four refinement iterations (~100 launches) are one CUDA
+    graph per (B, S)."""
+
+    def __init__(self, sd, prefix="camera_head.", trunk_depth=4, num_heads=16, device="cuda"):
+        from . import ops
+        self.ops = ops
+        dev = torch.device(device)
+        raw = {k[len(prefix):]: v.detach() for k, v in sd.items() if k.startswith(prefix)}
+        self.w16 = {k[:-len(".weight")]: v.to(device=dev, dtype=torch.float16).contiguous()
+                    for k, v in raw.items() if k.endswith(".weight") and v.dim() == 2 and v.shape[1] % 8 == 0}
+        self.f32 = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in raw.items()}
+        self.trunk_depth, self.heads, self.device = trunk_depth, num_heads, dev
+        self._graphs = {}
+        self.use_cuda_graph = True
+
+    def _iterations(self, tokens, num_iterations):
+        ops, w16, f = self.ops, self.w16, self.f32
+        B, S, C = tokens.shape
+        M, nh = B * S, self.heads
+        x0 = ops.layernorm_f32(tokens.reshape(M, C), f["token_norm.weight"], f["token_norm.bias"], eps=1e-5)
+        pred, outs = None, []
+        for _ in range(num_iterations):
+            inp = f["empty_pose_tokens"].expand(B, S, -1).reshape(M, -1) if pred is None else pred
+            # embed_pose: K = 9 (not a GEMV shape): one small float32 matmul, as plumbing
+            emb = torch.addmm(f["embed_pose.bias"], inp, f["embed_pose.weight"].t())
+            mod = ops.gemv_f32(w16["poseLN_modulation.1"], f["poseLN_modulation.1.bias"], emb, silu_in=True)
+            shift, scale, gate = mod[:, :C], mod[:, C:2 * C], mod[:, 2 * C:]
+            x = ops.layernorm_f32(x0, eps=1e-6, shift=shift, scale=scale, gate=gate)
+            for i in range(self.trunk_depth):
+                p = f"trunk.{i}."
+                h = ops.layernorm_f32(x, f[p + "norm1.weight"], f[p + "norm1.bias"], eps=1e-5)
+                qkv = ops.gemv_f32(w16[p + "attn.qkv"], f[p + "attn.qkv.bias"], h)
+                o = ops.small_attention_f32(qkv, B, S, nh, C // nh)
+                x = ops.gemv_f32(w16[p + "attn.proj"], f[p + "attn.proj.bias"], o, residual=x, gamma=f[p + "ls1.gamma"])
+                h = ops.layernorm_f32(x, f[p + "norm2.weight"], f[p + "norm2.bias"], eps=1e-5)
+                h = ops.gemv_f32(w16[p + "mlp.fc1"], f[p + "mlp.fc1.bias"], h, gelu_out=True)
+                x = ops.gemv_f32(w16[p + "mlp.fc2"], f[p + "mlp.fc2.bias"], h, residual=x, gamma=f[p + "ls2.gamma"])
+            h = ops.layernorm_f32(x, f["trunk_norm.weight"], f["trunk_norm.bias"], eps=1e-5)
+            h = ops.gemv_f32(w16["pose_branch.fc1"], f["pose_branch.fc1.bias"], h, gelu_out=True)
+            delta = torch.addmm(f["pose_branch.fc2.bias"], h, f["pose_branch.fc2.weight"].t())      # N = 9
+            pred = delta if pred is None else pred + delta
+            outs.append(torch.cat([pred[:, :7], F.relu(pred[:, 7:])], dim=-1).view(B, S, -1))
+        return outs
+
+    @torch.no_grad()
+    def __call__(self, aggregated_tokens_list, num_iterations=4):
+        tokens = aggregated_tokens_list[-1][:, :, 0].float().contiguous()     # [B, S, 2C]: the camera token of the last layer
+        if not self.use_cuda_graph:
+            return self._iterations(tokens, num_iterations)
+        key = (tuple(tokens.shape), num_iterations)
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(x=tokens.clone())
+            side = torch.cuda.Stream(tokens.device)
+            side.wait_stream(torch.cuda.current_stream(tokens.device))
+            with torch.cuda.stream(side):
+                self._iterations(st["x"], num_iterations)
+            torch.cuda.current_stream(tokens.device).wait_stream(side)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                st["out"] = self._iterations(st["x"], num_iterations)
+            g = (cg, st)
+            self._graphs = {key: g}
+        cg, st = g
+        st["x"].copy_(tokens)
+        cg.replay()
+        return [o.clone() for o in st["out"]]
+
+
 def _uv_embed(x, W, H, ratio=0.1):
     """_apply_pos_embed (dpt_head.py:249-259) with create_uv_grid / position_grid_to_embed (heads/utils.py)."""
     pw, ph, C = x.shape[-1], x.shape[-2], x.shape[1]
@@ -197,7 +269,8 @@ class VGGT:
 
     def load_state_dict(self, sd, strict=True):
         self.aggregator.load_state_dict(sd, prefix="aggregator.")
-        self.camera_head = CameraHead(sd, device=self.device, **self._ck)
+        head = CameraHeadR3G if self.device.type == "cuda" else CameraHead     # the torch mirror is the CPU / oracle side
+        self.camera_head = head(sd, device=self.device, **self._ck)
         self.depth_head = DPTHead(sd, patch_size=self.patch_size, device=self.device, **self._dk)
         return self
 

@@ -216,6 +216,26 @@ int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width
                    const void* ln_b, const void* w_out, const void* b_out, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * VGGT camera head (vggt/vggt/heads/camera_head.py:73-141).  The reference runs it in float32 outside autocast on S pose
+ * tokens (S = frames), so every nn.Linear is a GEMV over its weight matrix (HBM-bound): weights fp16, everything else
+ * float32.
+ *   r3g_gemv_f32:  out[b,n] = res[b,n] + gamma[n] * g( W[n,:] . a(vec[b,:]) + bias[n] )   (res, gamma, bias optional;
+ *       a = SiLU if act_in == 1 (poseLN_modulation, :113), g = exact GELU if act_out == 1 (Mlp fc1, vggt/layers/mlp.py:22);
+ *       res + gamma * y is Block's LayerScale residual, vggt/layers/block.py:77-98).  B <= 8 rows, K % 8 == 0.
+ *   r3g_layernorm_f32:  y = LN(x; w, b, eps); with shift / scale / gate (float32 [rows, >= width], stride mod_ld):
+ *       y = gate * (LN(x) * (1 + scale) + shift) + x   (camera_head.py:116-120).
+ *   r3g_small_attention_f32:  softmax(q k^T * scale) v over S <= 64 tokens, qkv float32 [B*S, 3*H*D] laid out (3, H, D)
+ *       (vggt/layers/attention.py:52-61), out float32 [B*S, H*D]; D in {32, 64, 128, 256} (the trunk has 16 heads of 128). */
+int r3g_gemv_f32(r3g_ctx* ctx, const void* w_f16, const float* bias, const float* vec, int64_t vec_ld, float* out,
+                 int64_t out_ld, const float* residual, const float* gamma, int B, int N, int K, int act_in, int act_out,
+                 void* stream);
+int r3g_layernorm_f32(r3g_ctx* ctx, const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int width, float eps,
+                      const float* w, const float* b, const float* shift, const float* scale, const float* gate,
+                      int64_t mod_ld, void* stream);
+int r3g_small_attention_f32(r3g_ctx* ctx, const float* qkv, float* out, int B, int S, int H, int D, float scale,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Back-projection.  Replaces the per-pixel work of unproject_depth_map_to_point_map
  * (vggt/vggt/utils/geometry.py:15-117): depth float32 [S,H,W] on the device (the reference squeezes a trailing 1).
  * cam_to_world_host: float64 [S,3,4] = rows 0..2 of closed_form_inverse_se3(extrinsic) (geometry.py:74-77) --

@@ -39,7 +39,7 @@ def _worker(rank, world, port, q):
         q.put((mine, len(got)))
     # streaming gather: one fixed-capacity message per rank and step, ring of depth 2, uneven object counts
     from r3g.dist import MeshStreamGatherer
-    sg = MeshStreamGatherer(cap_vertices=16, cap_faces=32, device="cpu")
+    sg = MeshStreamGatherer(cap_vertices=8 + 8 * rank, cap_faces=32 - 8 * rank, device="cpu")   # ranks agree on the max
     for step in range(4):
         if step < len(meshes):
             sg.submit(*meshes[step])

@@ -123,3 +123,44 @@ def test_run_vggt_composite_against_cpu_oracle():
     assert rel_l2(dmap, dr[0]) < 1e-2 and rel_l2(conf, cr[0]) < 1e-2
     ref_pts = R.unproject_depth_map_to_point_map(dmap.cpu().numpy(), E, K)
     assert pts.dtype == np.float64 and np.array_equal(pts, ref_pts)      # the back-projection itself is exact
+
+
+def test_camera_head_on_r3g_kernels_against_the_torch_mirror():
+    """row v4: CameraHeadR3G (fp16 weights, float32 activations, GEMV / LayerNorm / small-attention kernels, one CUDA graph)
+    vs the float32 torch mirror that tests/test_oracle_golden.py pins against the reference module -- full geometry
+    (2048 wide, 16 heads of 128, 4 trunk blocks, 4 iterations) and a small one; graph replay == eager."""
+    from r3g import ops
+    from r3g.vggt_heads import CameraHead, CameraHeadR3G, random_state_dict
+    # the three kernels alone
+    torch.manual_seed(0)
+    w = (torch.randn(96, 64, device="cuda") * 0.1)
+    b, x, res, gm = (torch.randn(*s, device="cuda") for s in ((96,), (3, 64), (3, 96), (96,)))
+    got = ops.gemv_f32(w.half(), b, x, residual=res, gamma=gm, silu_in=True, gelu_out=True)
+    ref = res + gm * torch.nn.functional.gelu(torch.nn.functional.silu(x) @ w.half().float().t() + b)
+    assert (got - ref).abs().max().item() < 1e-4
+    xs = torch.randn(5, 200, device="cuda")
+    lw, lb, sh, sc, gt = (torch.randn(*s, device="cuda") for s in ((200,), (200,), (5, 200), (5, 200), (5, 200)))
+    ln = torch.nn.functional.layer_norm
+    assert (ops.layernorm_f32(xs, lw, lb, eps=1e-5) - ln(xs, (200,), lw, lb, 1e-5)).abs().max().item() < 1e-4
+    assert (ops.layernorm_f32(xs, eps=1e-6, shift=sh, scale=sc, gate=gt)
+            - (gt * (ln(xs, (200,), eps=1e-6) * (1 + sc) + sh) + xs)).abs().max().item() < 1e-4
+    qkv = torch.randn(2 * 5, 3 * 4 * 128, device="cuda")
+    q, k, v = qkv.view(2, 5, 3, 4, 128).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(10, 512)
+    assert (ops.small_attention_f32(qkv, 2, 5, 4, 128) - ref).abs().max().item() < 1e-4
+    # the whole head
+    for C, heads, trunk in ((1024, 16, 4), (128, 2, 2)):
+        sd = random_state_dict(7, embed_dim=C, depth=1, vit_depth=1, trunk_depth=trunk, features=32,
+                               out_channels=(32, 64, 128, 128), img_size=56)
+        sd = {k: v for k, v in sd.items() if k.startswith("camera_head.")}
+        mine = CameraHeadR3G(sd, trunk_depth=trunk, num_heads=heads)
+        mirror = CameraHead({k: (v.half().float() if v.dim() == 2 and v.shape[1] % 8 == 0 else v) for k, v in sd.items()},
+                            trunk_depth=trunk, num_heads=heads, device="cuda")
+        toks = [torch.randn(1, 2, 7, 2 * C, device="cuda")]
+        a = mine(toks)
+        b_ = mirror(toks)
+        mine.use_cuda_graph = False
+        c = mine(toks)
+        for x1, x2, x3 in zip(a, b_, c):
+            assert torch.equal(x1, x3), "graph replay must equal the eager launches"
+            assert (x1 - x2).abs().max().item() < 2e-3 * max(1.0, x2.abs().max().item())
