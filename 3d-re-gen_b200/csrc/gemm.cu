@@ -158,6 +158,9 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, const uint
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_f(__half2float(__float2half_rn(f[j])));  // Linear output is fp16
+      } else if (p.act == 3) {   // ReLU (the DPT head's convolutions, dpt_head.py:344-392)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(__half2float(__float2half_rn(f[j])));

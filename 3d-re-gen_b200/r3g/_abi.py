@@ -75,6 +75,8 @@ SIGNATURES = {
     "r3g_points_fourier": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
     "r3g_points_fourier_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
     "r3g_lnpost_dot": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "r3g_im2col3x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "r3g_bilinear_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "r3g_gemv_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "r3g_layernorm_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "r3g_small_attention_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

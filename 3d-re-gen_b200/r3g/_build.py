@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(PKG_DIR))
 CSRC = os.path.join(os.path.dirname(PKG_DIR), "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libr3g.so")
 
-CU_SOURCES = ["ctx.cu", "mc.cu", "mesh.cu", "rowops.cu", "heads.cu", "gemm.cu", "attn.cu"]
+CU_SOURCES = ["ctx.cu", "mc.cu", "mesh.cu", "rowops.cu", "heads.cu", "conv.cu", "gemm.cu", "attn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

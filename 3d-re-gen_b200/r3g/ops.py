@@ -9,7 +9,7 @@ import torch
 
 from . import _abi
 
-ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 
 
 _call_device = None   # device of the op being issued (set by _ctx, read by _stream; contexts are not thread-safe)
@@ -343,6 +343,33 @@ def lnpost_dot(x, ln_w, ln_b, w_out, b_out, out, eps=1e-5):
     x2, rows, width, ldx, _, _ = _rows(x, "x")
     ctx.check(ctx.lib.r3g_lnpost_dot(ctx.handle, _p(x2), ldx, rows, width, float(eps), _p(ln_w), _p(ln_b), _p(w_out),
                                      _p(b_out), _p(out), _stream()))
+    return out
+
+
+def im2col3x3(x, stride=1, relu_in=False, out=None):
+    """x fp16 NHWC [N,H,W,C] -> rows [N*Ho*Wo, 9*C] for a 3x3 / padding-1 convolution as a GEMM (see r3g.h)."""
+    _f16(x, "x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("im2col3x3: x must be a contiguous NHWC tensor")
+    ctx = _ctx(x)
+    N, H, W, Cc = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty(N * Ho * Wo, 9 * Cc, device=x.device, dtype=torch.float16)
+    ctx.check(ctx.lib.r3g_im2col3x3(ctx.handle, _p(x), _p(out), N, H, W, Cc, int(stride), int(relu_in), _stream()))
+    return out, Ho, Wo
+
+
+def bilinear_nhwc(x, Ho, Wo, out=None):
+    """F.interpolate(..., mode='bilinear', align_corners=True) on an fp16 NHWC tensor."""
+    _f16(x, "x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("bilinear_nhwc: x must be a contiguous NHWC tensor")
+    ctx = _ctx(x)
+    N, Hi, Wi, Cc = x.shape
+    if out is None:
+        out = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.float16)
+    ctx.check(ctx.lib.r3g_bilinear_nhwc(ctx.handle, _p(x), _p(out), N, Hi, Wi, int(Ho), int(Wo), Cc, _stream()))
     return out
 
 

@@ -82,8 +82,8 @@ int r3g_mesh_components(r3g_ctx* ctx, const int32_t* faces, int64_t nf, int64_t 
  *   This is how the txt / img streams of DoubleStreamBlock (one segment per batch element) live inside one
  *   joint [B, Ltxt+Limg, ...] buffer without any torch.cat (hunyuan3ddit.py:205-211,396); the caller offsets
  *   the x / y pointers to the first row of the stream.
- *   act: 0 none, 1 tanh-GELU (hunyuan3ddit.py:63-69), 2 erf-GELU (attention_blocks.py:178); applied to
- *        output columns [act_col0, act_col1) only.
+ *   act: 0 none, 1 tanh-GELU (hunyuan3ddit.py:63-69), 2 erf-GELU (attention_blocks.py:178), 3 ReLU (the DPT head's
+ *        convolutions, vggt/heads/dpt_head.py:344-392); applied to output columns [act_col0, act_col1) only.
  *   gate/residual: if residual != NULL,  Y = residual + gate[b, n] * (acc + bias)  with b = r / gate_rows
  *        (gate == NULL means gate 1; gate_ld is the stride between batches in halfs), covering the gated
  *        residuals of hunyuan3ddit.py:212-216,267 and the plain residuals of attention_blocks.py:296-299.
@@ -214,6 +214,15 @@ int r3g_points_fourier_f32(r3g_ctx* ctx, const float* queries, void* out, int64_
  * (attention_blocks.py:491-493), written to the float32 grid at out[r]. */
 int r3g_lnpost_dot(r3g_ctx* ctx, const void* x, int64_t ldx, int rows, int width, float eps, const void* ln_w,
                    const void* ln_b, const void* w_out, const void* b_out, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VGGT DPT depth head (vggt/vggt/heads/dpt_head.py:172-291) on channels-last fp16 feature maps: 1x1 convolutions and the
+ * kernel == stride transposed convolutions are r3g_linear on the [N*H*W, C] rows; a 3x3 convolution (padding 1) is
+ *   r3g_im2col3x3: cols[(n,yo,xo), (ky*3+kx)*C + c] = relu?(x[n, yo*stride+ky-1, xo*stride+kx-1, c]) (0 outside) -> r3g_linear
+ * with the weight permuted to [C_out, (ky, kx, C_in)]; Ho = (H - 1) / stride + 1.  r3g_bilinear_nhwc is
+ * F.interpolate(mode="bilinear", align_corners=True) (custom_interpolate, dpt_head.py:459-484).  C % 8 == 0. */
+int r3g_im2col3x3(r3g_ctx* ctx, const void* x, void* cols, int N, int H, int W, int C, int stride, int relu_in, void* stream);
+int r3g_bilinear_nhwc(r3g_ctx* ctx, const void* x, void* out, int N, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VGGT camera head (vggt/vggt/heads/camera_head.py:73-141).  The reference runs it in float32 outside autocast on S pose

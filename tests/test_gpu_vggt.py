@@ -164,3 +164,56 @@ def test_camera_head_on_r3g_kernels_against_the_torch_mirror():
         for x1, x2, x3 in zip(a, b_, c):
             assert torch.equal(x1, x3), "graph replay must equal the eager launches"
             assert (x1 - x2).abs().max().item() < 2e-3 * max(1.0, x2.abs().max().item())
+
+
+def test_conv_kernels_against_torch():
+    """im2col3x3 + linear == F.conv2d (stride 1 and 2, ReLU epilogue, residual), bilinear_nhwc == F.interpolate
+    (align_corners=True), on channels-last fp16."""
+    import torch.nn.functional as F
+    from r3g import ops
+    torch.manual_seed(0)
+    N, H, W, C, Co = 2, 13, 17, 64, 96
+    x = torch.randn(N, H, W, C, device="cuda").half()
+    wt = (torch.randn(Co, C, 3, 3, device="cuda") * 0.05).half()
+    b = (torch.randn(Co, device="cuda") * 0.1).half()
+    wm = wt.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    for stride in (1, 2):
+        cols, Ho, Wo = ops.im2col3x3(x, stride=stride)
+        y = ops.linear(cols, wm, b, act=ops.ACT_RELU).view(N, Ho, Wo, Co)
+        ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), b.float(), stride=stride, padding=1)).permute(0, 2, 3, 1)
+        assert y.shape == ref.shape and (y.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    cols, Ho, Wo = ops.im2col3x3(x, relu_in=True)
+    res = torch.randn(N * H * W, Co, device="cuda").half()
+    y = ops.linear(cols, wm, b, residual=res)
+    ref = F.conv2d(F.relu(x.permute(0, 3, 1, 2).float()), wt.float(), b.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Co) + res.float()
+    assert (y.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    for size in ((26, 34), (19, 23), (13, 17)):
+        got = ops.bilinear_nhwc(x, *size)
+        ref = F.interpolate(x.permute(0, 3, 1, 2).float(), size=size, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        assert (got.float() - ref).abs().max().item() < 4e-3
+
+
+def test_dpt_head_on_r3g_kernels_against_the_torch_mirror():
+    """row v6: DPTHeadR3G (every convolution a tcgen05 GEMM over NHWC fp16) vs the float32 torch mirror that
+    tests/test_oracle_golden.py pins against the reference module; the real channel widths at a 70 x 84 image, and a
+    small one.  Graph replay == eager."""
+    from r3g.vggt_heads import DPTHead, DPTHeadR3G, random_state_dict
+    for C, feats, ocs, hw in ((1024, 256, (256, 512, 1024, 1024), (70, 84)), (128, 32, (32, 64, 128, 128), (56, 56))):
+        sd = random_state_dict(5, embed_dim=C, depth=1, vit_depth=1, trunk_depth=1, features=feats, out_channels=ocs, img_size=56)
+        sd = {k: v.half().float() for k, v in sd.items() if k.startswith("depth_head.")}
+        H, W = hw
+        P = (H // 14) * (W // 14)
+        torch.manual_seed(1)
+        toks = [torch.randn(1, 2, 5 + P, 2 * C, device="cuda") for _ in range(2)]
+        imgs = torch.rand(1, 2, 3, H, W, device="cuda")
+        kw = dict(intermediate_layer_idx=(0, 1, 0, 1))
+        mine, mirror = DPTHeadR3G(sd, **kw), DPTHead(sd, device="cuda", **kw)
+        d1, c1 = mine(toks, imgs, 5)
+        d2, c2 = mirror(toks, imgs, 5)
+        mine.use_cuda_graph = False
+        d3, c3 = mine(toks, imgs, 5)
+        assert d1.shape == d2.shape == (1, 2, H, W, 1) and c1.shape == c2.shape == (1, 2, H, W)
+        assert torch.equal(d1, d3) and torch.equal(c1, c3), "graph replay must equal the eager launches"
+        e_d, e_c = rel_l2(d1, d2), rel_l2(c1, c2)
+        print(f"DPT on r3g kernels, width {C}: depth rel-L2 {e_d:.2e}, confidence rel-L2 {e_c:.2e}")
+        assert e_d < 1e-2 and e_c < 1e-2
