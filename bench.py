@@ -16,10 +16,13 @@ Workloads (`config.workload` names the BASELINE.json config each one is):
 `e2e`    : objects/s through the public call `pipe(image=<PIL RGBA>, ..., output_type="mesh")` with host buffers: the
            image processor, the pinned host -> device copy of the crop and the device -> host landing of the mesh
            (pinned ring, r3g.dist.MeshStreamGatherer) are inside the timed region, every step.
-The two arms are INTERLEAVED object by object inside one barrier-bracketed region (device-resident object, then
-end-to-end object, K times) and each arm's time is the sum of its own CUDA-event segments, so both see the same clocks.
-Objects are independent (src/2d_to_3d_models/run.py:188-193 shards them over GPUs): no data-path collective; the finished
-meshes stream to rank 0 over NCCL on a side stream while the next object computes.
+On one GPU the two arms are INTERLEAVED object by object inside one barrier-bracketed region (device-resident object,
+then end-to-end object, K times) and each arm's time is the sum of its own CUDA-event segments, so both see the same
+clocks.  On N > 1 GPUs the arms run one after the other: the device-resident arm packs its meshes into a staging buffer and
+moves them to rank 0 in one NCCL message per peer at the end (inside its timed region); the end-to-end arm does the same
+and then lands every mesh in rank 0's pinned host ring (on one GPU each mesh streams there as it finishes, under the next
+object's compute).
+Objects are independent (src/2d_to_3d_models/run.py:188-193 shards them over GPUs): no data-path collective.
 """
 import argparse
 import json
@@ -287,7 +290,7 @@ def main_shapegen(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     from r3g import _abi
-    from r3g.dist import MeshStreamGatherer
+    from r3g.dist import MeshBatchGatherer, MeshStreamGatherer
     from r3g.pipelines import Hunyuan3DDiTFlowMatchingPipeline
 
     pk = peaks()
@@ -337,50 +340,80 @@ def main_shapegen(args):
 
     def count(step, r, v, f):          # consumer thread of the e2e gatherer on rank 0: bytes that landed on the host
         d2h_bytes[0] += v.numel() * 4 + f.numel() * 4
-    g_dev = MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=False, sink=lambda *a: None) if world > 1 else None
-    g_e2e = MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=True, sink=count)
+    # device-resident arm at N > 1: meshes are packed into a per-rank staging buffer and moved to rank 0 in ONE message
+    # per peer at the end of the arm (no NCCL kernel is resident while objects compute); e2e arm: per-object streaming
+    # gather on a side stream into rank 0's pinned ring
+    # (one GPU: each mesh streams to the pinned host ring as it finishes, under the next object's compute).  A per-object
+    # NCCL exchange during compute cost ~0.15 s per object at N = 8 (profiles/README.md r2d), so at N > 1 BOTH arms
+    # keep NVLink quiet while objects compute and pay the gather -- and, for e2e, the pinned D2H of all meshes on rank 0 --
+    # once, inside their timed regions.
+    g_dev = MeshBatchGatherer(cap_v, cap_f, K, f"cuda:{local}") if world > 1 else None
+    g_e2e = (MeshBatchGatherer(cap_v, cap_f, K, f"cuda:{local}") if world > 1
+             else MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=True, sink=count))
+    interleave = world == 1            # one GPU: the two arms alternate object by object and see the same clocks
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
     launches0 = ctx.launches + pipe.replayed_launches
     h2d = 0
     meshes = []
-    barrier()
-    if args.profile_mode:
-        torch.cuda.nvtx.range_push("timed")      # ncu --nvtx --nvtx-include "timed/" profiles the timed object(s) only
-    ev[0].record()
-    for k in range(K):
+    seg_dev, seg_e2e = [], []
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def do_resident(k):
+        a = mark()
         m = object_resident(W + 2 * k)
         if g_dev is not None:
-            g_dev.submit(*( (m.mesh_v, m.mesh_f) if m is not None else (None, None)))
-        ev[2 * k + 1].record()
+            g_dev.submit(*((m.mesh_v, m.mesh_f) if m is not None else (None, None)))
+        seg_dev.append((a, mark()))
         if k == 0:      # only the first mesh is kept (for the line's statistics): holding all K would make every later
             meshes.append(m)    # object cudaMalloc fresh ~200 MB blocks (100 ms each) inside the timed region
-        del m
-        if args.profile_mode:
-            ev[2 * k + 2].record()
-            continue
+
+    def do_e2e(k):
+        nonlocal h2d
+        a = mark()
         m2 = object_e2e(W + 2 * k + 1)
         h2d += dev_in[0].numel() * 4
         g_e2e.submit(*((m2.mesh_v, m2.mesh_f) if m2 is not None else (None, None)))
-        del m2
-        ev[2 * k + 2].record()
+        seg_e2e.append((a, mark()))
+
+    barrier()
+    if args.profile_mode:
+        torch.cuda.nvtx.range_push("timed")      # ncu --nvtx --nvtx-include "timed/" profiles the timed object(s) only
+    if interleave:
+        for k in range(K):
+            do_resident(k)
+            if not args.profile_mode:
+                do_e2e(k)
+    else:
+        for k in range(K):
+            do_resident(k)
     if args.profile_mode:
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_pop()
+    a = mark()
     if g_dev is not None:
-        g_dev.finish()
-    ev_dev_end = torch.cuda.Event(enable_timing=True)
-    ev_dev_end.record()
-    g_e2e.finish()                      # the last object's mesh has landed on rank 0's host
-    ev_end = torch.cuda.Event(enable_timing=True)
-    ev_end.record()
+        g_dev.finish()                  # one NCCL message per peer: every rank's K meshes are on rank 0's device
+    seg_dev.append((a, mark()))
+    if not interleave and not args.profile_mode:
+        barrier()
+        for k in range(K):
+            do_e2e(k)
+    a = mark()
+    if world > 1:
+        g_e2e.finish(to_host=True, sink=count)   # every rank's meshes gathered to rank 0 and landed in its pinned ring
+    else:
+        g_e2e.finish()                  # the last object's mesh has landed on rank 0's host
+    seg_e2e.append((a, mark()))
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    ms_dev = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)) + ev[2 * K].elapsed_time(ev_dev_end)
-    ms_e2e = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)) + ev_dev_end.elapsed_time(ev_end)
+    ms_dev = sum(x.elapsed_time(y) for x, y in seg_dev)
+    ms_e2e = sum(x.elapsed_time(y) for x, y in seg_e2e)
     launches = (ctx.launches + pipe.replayed_launches - launches0)
     t = torch.tensor([ms_dev, ms_e2e], device="cuda")
     if world > 1:

@@ -52,6 +52,19 @@ def _worker(rank, world, port, q):
             assert torch.equal(v, gv) and torch.equal(f, gf)
     else:
         assert streamed == []
+    # batch gather (bench.py at N > 1): staging buffer per rank, one message per peer at the end, pinned-ring landing
+    from r3g.dist import MeshBatchGatherer
+    bg = MeshBatchGatherer(cap_vertices=8 + 8 * rank, cap_faces=32 - 8 * rank, steps=4, device="cpu")
+    for step in range(4):
+        bg.submit(*(meshes[step] if step < len(meshes) else (None, None)))
+    landed = []
+    bufs = bg.finish(to_host=True, sink=lambda k, r, v, f: landed.append((r, k, v.clone(), f.clone())))
+    if rank == 0:
+        assert len(bufs) == world and len(landed) == 7
+        for (r, k, v, f), (gv, gf) in zip(sorted(landed, key=lambda t: (t[0], t[1])), got):
+            assert torch.equal(v, gv) and torch.equal(f, gf)
+    else:
+        assert bufs == [] and landed == []
     # a rank with nothing to send must not deadlock the gather
     got2 = gather_meshes(meshes if rank == 0 else [])
     if rank == 0:
