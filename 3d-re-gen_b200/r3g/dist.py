@@ -203,6 +203,7 @@ class MeshStreamGatherer:
         self.send = [torch.empty(self.cap, **i32) for _ in range(depth)]
         self.results, self.sink = {}, sink
         self.pending = []            # rank 0: steps whose headers have been requested but whose payloads are not read yet
+        self._slot_done = [None] * depth   # event after which a send slot may be repacked (transfer / host copy done)
         if self.rank == 0:
             self.recv = [[torch.empty(self.cap, **i32) for _ in range(self.world - 1)] for _ in range(depth)]
             pin = self.cuda
@@ -264,6 +265,7 @@ class MeshStreamGatherer:
                     self.land[slot][r][:n].copy_(src[:n], non_blocking=True)
                 event = torch.cuda.Event()
                 event.record(self.side)
+                self._slot_done[slot] = event
         elif self.to_host:
             for r, (nv, nf) in enumerate(sizes):
                 n = 4 + 3 * nv + 3 * nf
@@ -271,6 +273,7 @@ class MeshStreamGatherer:
         elif self.cuda:          # device-resident consumer: it must still see the transfers of this step completed
             event = torch.cuda.Event()
             event.record(self.side)
+            self._slot_done[slot] = event
         self.q.put((step, slot, event, sizes))
 
     # ------------------------------------------------------------------------------------------------ API
@@ -285,10 +288,16 @@ class MeshStreamGatherer:
             # the slot's previous occupant (step - depth) must have left the pinned ring
             self.slot_free[slot].wait()
             self.slot_free[slot].clear()
+        # the mesh is copied into the ring slot on the CALLER's stream (a 150 MB device copy, ~50 us): its tensors are free
+        # again at once -- tying them to the side stream (record_stream) kept their ~200 MB blocks out of the caching
+        # allocator until the host copy had finished, and the next object's marching cubes paid a cudaMalloc (~100 ms)
+        if self.cuda:
+            if self._slot_done[slot] is not None:       # the slot's previous transfer / host copy must have left it
+                torch.cuda.current_stream(self.device).wait_event(self._slot_done[slot])
+        self._pack(self.send[slot], verts, faces)
         if self.cuda:
             self.side.wait_stream(torch.cuda.current_stream(self.device))
         with self._stream():
-            self._pack(self.send[slot], verts, faces)
             if self.world > 1:
                 if self.rank == 0:
                     works = dist.batch_isend_irecv([dist.P2POp(dist.irecv, self.recv[slot][r - 1], r)
@@ -306,12 +315,9 @@ class MeshStreamGatherer:
                     ev = torch.cuda.Event()
                     ev.record(self.side)
                 self.pending.append((step, slot, ev))     # its payloads are read at the next submit() / finish()
-        if self.cuda:
-            # a send buffer may be repacked only after its transfer: the NEXT use of this slot is ordered on the side
-            # stream; the caller's tensors (verts / faces) must outlive the copy: tie them to the side stream
-            for t in (verts, faces):
-                if t is not None and t.is_cuda:
-                    t.record_stream(self.side)
+            elif self.cuda:
+                self._slot_done[slot] = torch.cuda.Event()
+                self._slot_done[slot].record(self.side)   # the send has left this slot
 
     def finish(self):
         """Drain.  Returns, on rank 0, [(verts, faces)] ordered by (rank, step) -- gather_meshes' order; [] elsewhere."""

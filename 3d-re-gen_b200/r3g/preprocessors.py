@@ -9,8 +9,9 @@ from PIL import Image
 
 def array_to_tensor(np_array):
     """uint8 HxWxC -> float32 [1, C, H, W] in [-1, 1] (preprocessors.py:21-27)."""
-    t = torch.from_numpy(np.ascontiguousarray(np_array).astype(np.float32) / 255.0 * 2.0 - 1.0)
-    return t.permute(2, 0, 1)[None].contiguous()
+    a = np.ascontiguousarray(np_array).astype(np.float32) / 255.0 * 2.0 - 1.0
+    # channels-first in numpy: torch's strided permute().contiguous() of a [512,512,3] CPU tensor took 21 ms per call
+    return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))[None])
 
 
 class ImageProcessorV2:

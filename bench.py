@@ -30,6 +30,7 @@ import os
 import subprocess
 import sys
 import threading
+import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "3d-re-gen_b200")):
@@ -374,12 +375,18 @@ def main_shapegen(args):
         if k == 0:      # only the first mesh is kept (for the line's statistics): holding all K would make every later
             meshes.append(m)    # object cudaMalloc fresh ~200 MB blocks (100 ms each) inside the timed region
 
+    host = {"pipe_call_ms": 0.0, "gather_submit_ms": 0.0}      # host wall time of the two halves of an e2e step
+
     def do_e2e(k):
         nonlocal h2d
         a = mark()
+        t0 = time.perf_counter()
         m2 = object_e2e(W + 2 * k + 1)
+        t1 = time.perf_counter()
         h2d += dev_in[0].numel() * 4
         g_e2e.submit(*((m2.mesh_v, m2.mesh_f) if m2 is not None else (None, None)))
+        host["pipe_call_ms"] += 1e3 * (t1 - t0) / K
+        host["gather_submit_ms"] += 1e3 * (time.perf_counter() - t1) / K
         seg_e2e.append((a, mark()))
 
     barrier()
@@ -444,7 +451,7 @@ def main_shapegen(args):
             "config": shapegen_config(args, world, K),
             "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h_bytes[0] // (K * world) if world > 1 else d2h_bytes[0] // K,
-                    "d2h_bytes_total_on_rank0": d2h_bytes[0], "ms_per_step": ms_e2e / K,
+                    "d2h_bytes_total_on_rank0": d2h_bytes[0], "ms_per_step": ms_e2e / K, "host_ms_per_step": host,
                     "call": "pipe(image=<PIL RGBA>, ..., output_type='mesh') + mesh landed in pinned host memory on rank 0"},
             "gpu_launches": int(launches),
             "clocks": clk,
