@@ -99,7 +99,7 @@ class MeshBatchGatherer:
     object when the per-object exchange of MeshStreamGatherer overlapped the next object -- so the device-resident arm of
     bench.py keeps its NVLink traffic out of the compute phase."""
 
-    def __init__(self, cap_vertices, cap_faces, steps, device):
+    def __init__(self, cap_vertices, cap_faces, steps, device, to_host=False):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         caps = torch.tensor([int(cap_vertices), int(cap_faces)], dtype=torch.int64, device=device)
@@ -110,6 +110,24 @@ class MeshBatchGatherer:
         self.stage = torch.empty(steps, self.cap, dtype=torch.int32, device=device)
         self.stage[:, :4] = 0
         self.k = 0
+        # everything finish() needs exists before the first object: rank 0's receive buffers, the pinned ring, and the
+        # NCCL point-to-point connections (a first send / recv to a peer sets the channel up; done here on 4 words)
+        self.recv = ([torch.empty_like(self.stage) for _ in range(self.world - 1)] if self.rank == 0 else [])
+        self.ring = ([torch.empty(self.cap, dtype=torch.int32, pin_memory=self.stage.is_cuda) for _ in range(2)]
+                     if to_host and self.rank == 0 else None)
+        self._exchange(4)
+
+    def _exchange(self, words=None):
+        """Every peer's staging buffer (or its first `words` words of the first mesh) -> rank 0's receive buffers."""
+        if self.world == 1:
+            return
+        cut = (lambda b: b.view(-1)[:words]) if words else (lambda b: b)
+        if self.rank == 0:
+            ops = [dist.P2POp(dist.irecv, cut(self.recv[r - 1]), r) for r in range(1, self.world)]
+        else:
+            ops = [dist.P2POp(dist.isend, cut(self.stage), 0)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
     def submit(self, verts, faces):
         pack_mesh(self.stage[self.k], verts, faces, self.cap_v, self.cap_f)
@@ -120,21 +138,15 @@ class MeshBatchGatherer:
         buffers [world][K, cap] on the device; elsewhere [].  to_host: rank 0 then copies the USED words of every mesh
         through a two-slot pinned ring (copy engine, large transfers) and calls sink(step, rank, verts, faces) with views
         into the slot as each one lands."""
-        if self.world == 1:
-            bufs = [self.stage]
-        elif self.rank == 0:
-            bufs = [self.stage] + [torch.empty_like(self.stage) for _ in range(self.world - 1)]
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, bufs[r], r) for r in range(1, self.world)]):
-                w.wait()
-        else:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, self.stage, 0)]):
-                w.wait()
+        self._exchange()
+        if self.rank != 0:
             return []
+        bufs = [self.stage] + self.recv
         if not to_host:
             return bufs
         cuda = self.stage.is_cuda
         hdr = torch.stack([b[:, :2] for b in bufs]).cpu()             # [world, K, 2]: nv, nf of every mesh
-        ring = [torch.empty(self.cap, dtype=torch.int32, pin_memory=cuda) for _ in range(2)]
+        ring = self.ring or [torch.empty(self.cap, dtype=torch.int32, pin_memory=cuda) for _ in range(2)]
         done = [None, None]
         pending = []
 

@@ -349,7 +349,7 @@ def main_shapegen(args):
     # keep NVLink quiet while objects compute and pay the gather -- and, for e2e, the pinned D2H of all meshes on rank 0 --
     # once, inside their timed regions.
     g_dev = MeshBatchGatherer(cap_v, cap_f, K, f"cuda:{local}") if world > 1 else None
-    g_e2e = (MeshBatchGatherer(cap_v, cap_f, K, f"cuda:{local}") if world > 1
+    g_e2e = (MeshBatchGatherer(cap_v, cap_f, K, f"cuda:{local}", to_host=True) if world > 1
              else MeshStreamGatherer(cap_v, cap_f, device=f"cuda:{local}", to_host=True, sink=count))
     interleave = world == 1            # one GPU: the two arms alternate object by object and see the same clocks
 
