@@ -8,7 +8,12 @@
 //   * the first user of a grid edge is a pure function of the edge ("owner" cell, see owns_edge), so
 //     vertex ids = exclusive prefix sum over cells of the number of owned vertices + rank inside the cell,
 //   * face ids   = exclusive prefix sum over cells of the triangle count.
-// HBM-bound integer/byte work: one coalesced pass over the grid per kernel; no tensor cores.
+// HBM-bound integer/byte work, no tensor cores.  A warp owns 32 consecutive cells of one grid row (a "segment"); the
+// grid is read ONCE, coalesced, by the classify pass: every lane loads the four points of its own x, the sign bits go
+// through warp ballots, and only the lanes whose cell the surface crosses (cube index not 0 / 255) fetch the remaining
+// corners and run the Lewiner tests.  That pass leaves 16 bits per cell (tiling, number of owned vertices), so the two
+// emit passes never classify again: the vertex pass reads the corners of the cells that own vertices, the face pass
+// reads no grid values at all.
 #include <float.h>
 
 #include "r3g_internal.h"
@@ -20,10 +25,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
+constexpr int kWarps = kThreads / 32;
+
 struct McDims {
   int n0, n1, n2;   // grid points per axis (axis2 fastest)
   int c0, c1, c2;   // cells per axis
   int64_t ncells;
+  unsigned segs;    // 32-cell segments per row of c2 cells
+  unsigned nsegs;   // c0 * c1 * segs; segment s = (row, seg) in row-major order = the traversal order of the cells
 };
 
 struct Cell {
@@ -114,9 +123,9 @@ __device__ __forceinline__ int cube_index(const float* raw, float level) {
   return ci;
 }
 
-__device__ __forceinline__ Cell eval_cell(const float* raw, float level, double* cv, int x, int y, int z) {
+__device__ __forceinline__ Cell eval_cell(int ci, const float* raw, float level, double* cv, int x, int y, int z) {
   Cell c;
-  c.ci = cube_index(raw, level);
+  c.ci = ci;
   c.til = 0; c.nt = 0; c.nv = 0;
   if (c.ci == 0 || c.ci == 255) return c;
 #pragma unroll
@@ -159,28 +168,39 @@ __host__ __device__ __forceinline__ float ord2f(unsigned u) {
 #endif
 }
 
-// Block-wide exclusive scan of two counters in thread order; returns block totals in tot.
-__device__ __forceinline__ void block_scan2(unsigned a, unsigned b, unsigned& ea, unsigned& eb, unsigned& ta,
-                                            unsigned& tb) {
-  __shared__ unsigned wsa[kThreads / 32], wsb[kThreads / 32];
+// Block-wide exclusive scan in thread order (one or two counters); returns the block totals.
+template <int N>
+__device__ __forceinline__ void block_scan(const unsigned (&v)[N], unsigned (&excl)[N], unsigned (&total)[N]) {
+  __shared__ unsigned ws[N][kWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned ia = a, ib = b;
+  unsigned inc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) inc[k] = v[k];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    unsigned na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o);
-    if (lane >= o) { ia += na; ib += nb; }
-  }
-  if (lane == 31) { wsa[w] = ia; wsb[w] = ib; }
-  __syncthreads();
-  unsigned offa = 0, offb = 0, suma = 0, sumb = 0;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) {
-    if (i < w) { offa += wsa[i]; offb += wsb[i]; }
-    suma += wsa[i]; sumb += wsb[i];
+    for (int k = 0; k < N; ++k) {
+      unsigned n = __shfl_up_sync(0xffffffffu, inc[k], o);
+      if (lane >= o) inc[k] += n;
+    }
   }
-  ea = offa + ia - a;
-  eb = offb + ib - b;
-  ta = suma; tb = sumb;
+  if (lane == 31) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) ws[k][w] = inc[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    unsigned off = 0, sum = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) {
+      const unsigned t = ws[k][i];
+      if (i < w) off += t;
+      sum += t;
+    }
+    excl[k] = off + inc[k] - v[k];
+    total[k] = sum;
+  }
   __syncthreads();
 }
 
@@ -193,90 +213,147 @@ __device__ __forceinline__ bool cell_coords(const McDims& d, int64_t cell, int& 
   return true;
 }
 
-// Pass 1: per-block (vertex, triangle) counts and the volume's min/max (for skimage's level check).
-__global__ void __launch_bounds__(kThreads) mc_count_kernel(const float* __restrict__ g, McDims d, float level,
-                                                            unsigned* __restrict__ block_counts,
-                                                            float* __restrict__ block_minmax) {
-  const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  int x, y, z;
-  unsigned nv = 0, nt = 0;
-  float lo = INFINITY, hi = -INFINITY;
-  if (cell_coords(d, cell, x, y, z)) {
-    double cv[8];
-    float raw[8];
-    load_cell(g, d, x, y, z, raw);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { lo = fminf(lo, raw[i]); hi = fmaxf(hi, raw[i]); }
-    Cell c = eval_cell(raw, level, cv, x, y, z);
-    nv = c.nv; nt = c.nt;
-  }
-  unsigned ev, et, tv, tt;
-  block_scan2(nv, nt, ev, et, tv, tt);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-  }
-  __shared__ float slo[kThreads / 32], shi[kThreads / 32];
-  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 1; i < kThreads / 32; ++i) { lo = fminf(lo, slo[i]); hi = fmaxf(hi, shi[i]); }
-    block_counts[2 * blockIdx.x] = tv;
-    block_counts[2 * blockIdx.x + 1] = tt;
-    block_minmax[2 * blockIdx.x] = lo;      // no same-address atomics: the scan kernel reduces these
-    block_minmax[2 * blockIdx.x + 1] = hi;
-  }
+// The warp's segment: 32 consecutive cells (x0 .. x0+31) of row (y, z); warp-uniform.  Thread order inside a block =
+// segment order then lane = the sequential traversal order, so block scans over threads give traversal-order ranks.
+struct Segment {
+  bool valid;       // the segment exists
+  int x0, y, z;
+};
+__device__ __forceinline__ Segment warp_segment(const McDims& d) {
+  Segment sg;
+  const unsigned s = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5);
+  sg.valid = s < d.nsegs;
+  const unsigned row = s / d.segs;
+  sg.x0 = (int)(s - row * d.segs) * 32;
+  sg.z = (int)(row / (unsigned)d.c1);
+  sg.y = (int)(row - (unsigned)sg.z * (unsigned)d.c1);
+  return sg;
 }
 
-// Pass 2: exclusive scan of the per-block counts (single block; the array has ncells/256 entries).
-__global__ void __launch_bounds__(1024) mc_scan_kernel(const unsigned* __restrict__ counts,
-                                                       unsigned* __restrict__ offsets, int nblocks,
-                                                       const float* __restrict__ block_minmax,
+// info word of a cell: tiling (10 bits) | number of vertices the cell creates (4 bits)
+__device__ __forceinline__ unsigned short pack_info(int til, int nv) { return (unsigned short)(til | (nv << 10)); }
+
+// Pass 1: classify.  Per block: (vertex, triangle) counts and the min / max of the points it touched (for skimage's
+// level check); per cell of a block the surface crosses: the info word.
+__global__ void __launch_bounds__(kThreads) mc_count_kernel(const float* __restrict__ g, McDims d, float level,
+                                                            unsigned* __restrict__ block_counts,
+                                                            unsigned* __restrict__ block_minmax,
+                                                            unsigned short* __restrict__ info) {
+  const int lane = threadIdx.x & 31;
+  const Segment sg = warp_segment(d);
+  const int x = sg.x0 + lane;
+  const int64_t sy = d.n2, sz = (int64_t)d.n1 * d.n2;
+  const float* row = g + ((int64_t)sg.z * d.n1 + sg.y) * d.n2;      // point (0, y, z)
+  // own points: (x, y|y+1, z|z+1) for x <= c2 (= the last point of the row)
+  float v00 = level, v10 = level, v01 = level, v11 = level, ex = level;
+  float lo = INFINITY, hi = -INFINITY;
+  const bool point = sg.valid && x <= d.c2;
+  if (point) {
+    const float* p = row + x;
+    v00 = __ldg(p); v10 = __ldg(p + sy); v01 = __ldg(p + sz); v11 = __ldg(p + sz + sy);
+    lo = fminf(fminf(v00, v10), fminf(v01, v11));       // fminf / fmaxf skip NaNs (FlashVDM grids carry them)
+    hi = fmaxf(fmaxf(v00, v10), fmaxf(v01, v11));
+  }
+  // the four points at x0 + 32 (the x+1 corners of lane 31's cell): lanes 0..3 fetch one each
+  const bool has_extra = sg.valid && sg.x0 + 32 <= d.c2;
+  if (has_extra && lane < 4) {
+    ex = __ldg(row + (lane & 1 ? sy : 0) + (lane & 2 ? sz : 0) + sg.x0 + 32);
+    lo = fminf(lo, ex); hi = fmaxf(hi, ex);
+  }
+  const unsigned b00 = __ballot_sync(0xffffffffu, v00 > level), b10 = __ballot_sync(0xffffffffu, v10 > level);
+  const unsigned b01 = __ballot_sync(0xffffffffu, v01 > level), b11 = __ballot_sync(0xffffffffu, v11 > level);
+  const unsigned be = __ballot_sync(0xffffffffu, lane < 4 && ex > level);    // bit r: row r = (y + (r&1), z + (r>>1))
+  // two bits per row: own point, x+1 point
+  const unsigned t00 = __funnelshift_r(b00, (be >> 0) & 1u, lane) & 3u, t10 = __funnelshift_r(b10, (be >> 1) & 1u, lane) & 3u;
+  const unsigned t01 = __funnelshift_r(b01, (be >> 2) & 1u, lane) & 3u, t11 = __funnelshift_r(b11, (be >> 3) & 1u, lane) & 3u;
+  const int ci = (int)((t00 & 1u) | (t00 & 2u) | ((t10 & 2u) << 1) | ((t10 & 1u) << 3) | ((t01 & 1u) << 4) | ((t01 & 2u) << 4) |
+                       ((t11 & 2u) << 5) | ((t11 & 1u) << 7));
+  const bool cell = sg.valid && x < d.c2;
+  const bool active = cell && ci != 0 && ci != 255;
+
+  // min / max of the block (ordered-uint form, one redux per warp)
+  unsigned ulo = __reduce_min_sync(0xffffffffu, f2ord(lo)), uhi = __reduce_max_sync(0xffffffffu, f2ord(hi));
+  __shared__ unsigned slo[kWarps], shi[kWarps];
+  if (lane == 0) { slo[threadIdx.x >> 5] = ulo; shi[threadIdx.x >> 5] = uhi; }
+  const int any = __syncthreads_or(active);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < kWarps; ++i) { ulo = min(ulo, slo[i]); uhi = max(uhi, shi[i]); }
+    block_minmax[2 * blockIdx.x] = ulo;       // no same-address atomics: the scan kernel reduces these
+    block_minmax[2 * blockIdx.x + 1] = uhi;
+  }
+  if (!any) {       // the common case: the surface does not cross this block
+    if (threadIdx.x == 0) { block_counts[2 * blockIdx.x] = 0; block_counts[2 * blockIdx.x + 1] = 0; }
+    return;
+  }
+  unsigned cnt[2] = {0, 0};
+  unsigned short word = 0;
+  if (active) {
+    const float* p = row + x;
+    float raw[8];
+    raw[0] = v00; raw[3] = v10; raw[4] = v01; raw[7] = v11;
+    raw[1] = __ldg(p + 1); raw[2] = __ldg(p + sy + 1); raw[5] = __ldg(p + sz + 1); raw[6] = __ldg(p + sz + sy + 1);
+    double cv[8];
+    const Cell c = eval_cell(ci, raw, level, cv, x, sg.y, sg.z);
+    cnt[0] = c.nv; cnt[1] = c.nt;
+    word = pack_info(c.til, c.nv);
+  }
+  info[(int64_t)blockIdx.x * kThreads + threadIdx.x] = word;
+  unsigned excl[2], tot[2];
+  block_scan<2>(cnt, excl, tot);
+  if (threadIdx.x == 0) { block_counts[2 * blockIdx.x] = tot[0]; block_counts[2 * blockIdx.x + 1] = tot[1]; }
+}
+
+// Pass 2: exclusive scan of the per-block counts and reduction of the per-block min / max.  One block of 32 warps; warp w
+// owns a contiguous range of entries and walks it 32 at a time (coalesced 8-byte loads), twice: totals, then offsets.
+__global__ void __launch_bounds__(1024) mc_scan_kernel(const uint2* __restrict__ counts, uint2* __restrict__ offsets,
+                                                       int nblocks, const uint2* __restrict__ block_minmax,
                                                        int64_t* __restrict__ totals) {
   __shared__ unsigned long long sv[32], st[32];
-  __shared__ unsigned long long carry_v, carry_t;
-  if (threadIdx.x == 0) { carry_v = 0; carry_t = 0; }
-  __syncthreads();
+  __shared__ unsigned slo[32], shi[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float lo = INFINITY, hi = -INFINITY;
-  for (int base = 0; base < nblocks; base += 1024) {
-    int i = base + threadIdx.x;
-    if (i < nblocks) { lo = fminf(lo, block_minmax[2 * i]); hi = fmaxf(hi, block_minmax[2 * i + 1]); }
-    unsigned long long a = (i < nblocks) ? counts[2 * i] : 0, b = (i < nblocks) ? counts[2 * i + 1] : 0;
-    unsigned long long ia = a, ib = b;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o);
-      if (lane >= o) { ia += na; ib += nb; }
-    }
-    if (lane == 31) { sv[w] = ia; st[w] = ib; }
-    __syncthreads();
-    unsigned long long offa = carry_v, offb = carry_t;
-    for (int k = 0; k < w; ++k) { offa += sv[k]; offb += st[k]; }
-    if (i < nblocks) {
-      offsets[2 * i] = (unsigned)(offa + ia - a);
-      offsets[2 * i + 1] = (unsigned)(offb + ib - b);
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_v = offa + ia; carry_t = offb + ib; }
-    __syncthreads();
+  const int per = (((nblocks + 31) / 32) + 31) & ~31;      // entries per warp, a multiple of 32
+  const int begin = (int)min((long long)nblocks, (long long)w * per), end = (int)min((long long)nblocks, (long long)begin + per);
+  unsigned long long av = 0, at = 0;
+  unsigned lo = 0xffffffffu, hi = 0u;
+  for (int i = begin + lane; i < end; i += 32) {
+    const uint2 c = counts[i], m = block_minmax[i];
+    av += c.x; at += c.y;
+    lo = min(lo, m.x); hi = max(hi, m.y);
   }
-  __shared__ float slo[32], shi[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    av += __shfl_xor_sync(0xffffffffu, av, o);
+    at += __shfl_xor_sync(0xffffffffu, at, o);
   }
-  if (lane == 0) { slo[w] = lo; shi[w] = hi; }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0) { sv[w] = av; st[w] = at; slo[w] = lo; shi[w] = hi; }
   __syncthreads();
+  unsigned long long run_v = 0, run_t = 0, all_v = 0, all_t = 0;
+  for (int k = 0; k < 32; ++k) {
+    if (k < w) { run_v += sv[k]; run_t += st[k]; }
+    all_v += sv[k]; all_t += st[k];
+    lo = min(lo, slo[k]); hi = max(hi, shi[k]);
+  }
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    const uint2 c = i < end ? counts[i] : make_uint2(0u, 0u);
+    unsigned iv = c.x, it = c.y;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned nv = __shfl_up_sync(0xffffffffu, iv, o), nt = __shfl_up_sync(0xffffffffu, it, o);
+      if (lane >= o) { iv += nv; it += nt; }
+    }
+    if (i < end) offsets[i] = make_uint2((unsigned)(run_v + iv - c.x), (unsigned)(run_t + it - c.y));
+    run_v += __shfl_sync(0xffffffffu, iv, 31);
+    run_t += __shfl_sync(0xffffffffu, it, 31);
+  }
   if (threadIdx.x == 0) {
-    for (int k = 1; k < 32; ++k) { lo = fminf(lo, slo[k]); hi = fmaxf(hi, shi[k]); }
-    totals[0] = (int64_t)carry_v;
-    totals[1] = (int64_t)carry_t;
-    totals[2] = (int64_t)f2ord(lo);
-    totals[3] = (int64_t)f2ord(hi);
+    totals[0] = (int64_t)all_v;
+    totals[1] = (int64_t)all_t;
+    totals[2] = (int64_t)lo;
+    totals[3] = (int64_t)hi;
   }
 }
 
@@ -296,24 +373,27 @@ struct Rescale {
 __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __restrict__ g, McDims d, float level,
                                                              const unsigned* __restrict__ block_offsets,
                                                              const unsigned* __restrict__ block_counts,
+                                                             const unsigned short* __restrict__ info,
                                                              int32_t* __restrict__ vid, float* __restrict__ verts,
                                                              Rescale rs) {
   if (block_counts[2 * blockIdx.x] == 0) return;  // nothing to emit in this block (the common case)
-  const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  int x = 0, y = 0, z = 0;
+  const unsigned word = info[(int64_t)blockIdx.x * kThreads + threadIdx.x];
+  const unsigned nv[1] = {word >> 10};
+  unsigned excl[1], tot[1];
+  block_scan<1>(nv, excl, tot);
+  if (nv[0] == 0) return;
+  const Segment sg = warp_segment(d);
+  const int x = sg.x0 + (threadIdx.x & 31), y = sg.y, z = sg.z;
+  const int til = word & 1023;
   double cv[8];
-  Cell c; c.ci = 0; c.til = 0; c.nt = 0; c.nv = 0;
-  const bool valid = cell_coords(d, cell, x, y, z);
-  if (valid) {
+  {
     float raw[8];
     load_cell(g, d, x, y, z, raw);
-    c = eval_cell(raw, level, cv, x, y, z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cv[i] = (double)raw[i] - (double)level;
   }
-  unsigned ev, et, tv, tt;
-  block_scan2(c.nv, c.nt, ev, et, tv, tt);
-  if (c.nv == 0) return;
-  unsigned id = block_offsets[2 * blockIdx.x] + ev;
-  const int t0 = r3g_mc_tiling_start[c.til], t1 = r3g_mc_tiling_start[c.til + 1];
+  unsigned id = block_offsets[2 * blockIdx.x] + excl[0];
+  const int t0 = r3g_mc_tiling_start[til], t1 = r3g_mc_tiling_start[til + 1];
   unsigned seen = 0;
   for (int t = t0; t < t1; ++t) {
     const int e = r3g_mc_tri[t];
@@ -358,28 +438,23 @@ __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __rest
   }
 }
 
-// Pass 4: faces, in cell order then tiling order, looking vertex ids up by grid edge.
-__global__ void __launch_bounds__(kThreads) mc_face_kernel(const float* __restrict__ g, McDims d, float level,
-                                                           const unsigned* __restrict__ block_offsets,
+// Pass 4: faces, in cell order then tiling order, looking vertex ids up by grid edge.  Reads no grid values.
+__global__ void __launch_bounds__(kThreads) mc_face_kernel(McDims d, const unsigned* __restrict__ block_offsets,
                                                            const unsigned* __restrict__ block_counts,
+                                                           const unsigned short* __restrict__ info,
                                                            const int32_t* __restrict__ vid,
                                                            int32_t* __restrict__ faces) {
   if (block_counts[2 * blockIdx.x + 1] == 0) return;
-  const int64_t cell = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  int x = 0, y = 0, z = 0;
-  Cell c; c.ci = 0; c.til = 0; c.nt = 0; c.nv = 0;
-  if (cell_coords(d, cell, x, y, z)) {
-    double cv[8];
-    float raw[8];
-    load_cell(g, d, x, y, z, raw);
-    c = eval_cell(raw, level, cv, x, y, z);
-  }
-  unsigned ev, et, tv, tt;
-  block_scan2(c.nv, c.nt, ev, et, tv, tt);
-  if (c.nt == 0) return;
-  int64_t fo = 3 * (int64_t)(block_offsets[2 * blockIdx.x + 1] + et);
-  const int t0 = r3g_mc_tiling_start[c.til], t1 = r3g_mc_tiling_start[c.til + 1];
-  for (int t = t0; t < t1; ++t) faces[fo++] = vid[edge_slot(d, r3g_mc_tri[t], x, y, z)];
+  const int til = info[(int64_t)blockIdx.x * kThreads + threadIdx.x] & 1023;
+  const int t0 = r3g_mc_tiling_start[til], t1 = r3g_mc_tiling_start[til + 1];
+  const unsigned nt[1] = {(unsigned)(t1 - t0) / 3u};
+  unsigned excl[1], tot[1];
+  block_scan<1>(nt, excl, tot);
+  if (nt[0] == 0) return;
+  const Segment sg = warp_segment(d);
+  const int x = sg.x0 + (threadIdx.x & 31);
+  int64_t fo = 3 * (int64_t)(block_offsets[2 * blockIdx.x + 1] + excl[0]);
+  for (int t = t0; t < t1; ++t) faces[fo++] = vid[edge_slot(d, r3g_mc_tri[t], x, sg.y, sg.z)];
 }
 
 __global__ void __launch_bounds__(kThreads) mc_case_kernel(const float* __restrict__ g, McDims d, float level,
@@ -394,9 +469,10 @@ __global__ void __launch_bounds__(kThreads) mc_case_kernel(const float* __restri
 
 struct McWorkspace {
   int32_t* vid;
+  unsigned short* info;
   unsigned* counts;
   unsigned* offsets;
-  float* minmax;
+  unsigned* minmax;
   int64_t* totals;
   int nblocks;
 };
@@ -406,7 +482,10 @@ int make_dims(r3g_ctx* ctx, int n0, int n1, int n2, McDims& d) {
   d.n0 = n0; d.n1 = n1; d.n2 = n2;
   d.c0 = n0 - 1; d.c1 = n1 - 1; d.c2 = n2 - 1;
   d.ncells = (int64_t)d.c0 * d.c1 * d.c2;
-  if ((d.ncells + kThreads - 1) / kThreads > 0x7fffffffLL) return r3g_fail(ctx, R3G_E_INVALID, "mc: grid too large");
+  d.segs = (unsigned)((d.c2 + 31) / 32);
+  const int64_t nsegs = (int64_t)d.c0 * d.c1 * d.segs;
+  if (nsegs > 0x7fffffffLL) return r3g_fail(ctx, R3G_E_INVALID, "mc: grid too large");
+  d.nsegs = (unsigned)nsegs;
   return R3G_OK;
 }
 
@@ -414,13 +493,14 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int carve(r3g_ctx* ctx, const McDims& d, void* ws, size_t ws_bytes, McWorkspace& w) {
   const int64_t npts = (int64_t)d.n0 * d.n1 * d.n2;
-  w.nblocks = (int)((d.ncells + kThreads - 1) / kThreads);
+  w.nblocks = (int)(((int64_t)d.nsegs + kWarps - 1) / kWarps);
   size_t off = 0;
   char* base = (char*)ws;
   w.vid = (int32_t*)(base + off);       off += align256(sizeof(int32_t) * 4 * (size_t)npts);
+  w.info = (unsigned short*)(base + off);  off += align256(sizeof(unsigned short) * kThreads * (size_t)w.nblocks);
   w.counts = (unsigned*)(base + off);   off += align256(sizeof(unsigned) * 2 * (size_t)w.nblocks);
   w.offsets = (unsigned*)(base + off);  off += align256(sizeof(unsigned) * 2 * (size_t)w.nblocks);
-  w.minmax = (float*)(base + off);      off += align256(sizeof(float) * 2 * (size_t)w.nblocks);
+  w.minmax = (unsigned*)(base + off);   off += align256(sizeof(unsigned) * 2 * (size_t)w.nblocks);
   w.totals = (int64_t*)(base + off);    off += 256;
   if (off > ws_bytes || !ws) return r3g_fail(ctx, R3G_E_WORKSPACE, "mc: workspace %zu < required %zu", ws_bytes, off);
   return R3G_OK;
@@ -431,9 +511,10 @@ int carve(r3g_ctx* ctx, const McDims& d, void* ws, size_t ws_bytes, McWorkspace&
 extern "C" size_t r3g_mc_workspace_bytes(int n0, int n1, int n2) {
   if (n0 < 2 || n1 < 2 || n2 < 2) return 0;
   const int64_t npts = (int64_t)n0 * n1 * n2;
-  const int64_t ncells = (int64_t)(n0 - 1) * (n1 - 1) * (n2 - 1);
-  const size_t nblocks = (size_t)((ncells + kThreads - 1) / kThreads);
-  return align256(sizeof(int32_t) * 4 * (size_t)npts) + 3 * align256(sizeof(unsigned) * 2 * nblocks) + 256;
+  const int64_t nsegs = (int64_t)(n0 - 1) * (n1 - 1) * ((n2 - 1 + 31) / 32);
+  const size_t nblocks = (size_t)((nsegs + kWarps - 1) / kWarps);
+  return align256(sizeof(int32_t) * 4 * (size_t)npts) + align256(sizeof(unsigned short) * kThreads * nblocks) +
+         3 * align256(sizeof(unsigned) * 2 * nblocks) + 256;
 }
 
 extern "C" int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level, void* workspace,
@@ -448,9 +529,9 @@ extern "C" int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int
   if (rc) return rc;
   rc = carve(ctx, d, workspace, workspace_bytes, w);
   if (rc) return rc;
-  mc_count_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.counts, w.minmax);
+  mc_count_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.counts, w.minmax, w.info);
   R3G_LAUNCH_OK(ctx);
-  mc_scan_kernel<<<1, 1024, 0, s>>>(w.counts, w.offsets, w.nblocks, w.minmax, w.totals);
+  mc_scan_kernel<<<1, 1024, 0, s>>>((const uint2*)w.counts, (uint2*)w.offsets, w.nblocks, (const uint2*)w.minmax, w.totals);
   R3G_LAUNCH_OK(ctx);
   R3G_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, w.totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   R3G_CUDA_OK(ctx, cudaStreamSynchronize(s));
@@ -487,9 +568,9 @@ extern "C" int r3g_mc_extract(r3g_ctx* ctx, const float* grid, int n0, int n1, i
     rs.size[a] = bounds_host ? bounds_host[3 + a] - bounds_host[a] : 1.0;
     rs.n[a] = (double)nax[a];
   }
-  mc_vertex_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.counts, w.vid, verts, rs);
+  mc_vertex_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.counts, w.info, w.vid, verts, rs);
   R3G_LAUNCH_OK(ctx);
-  mc_face_kernel<<<w.nblocks, kThreads, 0, s>>>(grid, d, level, w.offsets, w.counts, w.vid, faces);
+  mc_face_kernel<<<w.nblocks, kThreads, 0, s>>>(d, w.offsets, w.counts, w.info, w.vid, faces);
   R3G_LAUNCH_OK(ctx);
   return R3G_OK;
 }
@@ -502,6 +583,7 @@ extern "C" int r3g_mc_classify(r3g_ctx* ctx, const float* grid, int n0, int n1, 
   McDims d;
   int rc = make_dims(ctx, n0, n1, n2, d);
   if (rc) return rc;
+  if ((d.ncells + kThreads - 1) / kThreads > 0x7fffffffLL) return r3g_fail(ctx, R3G_E_INVALID, "mc: grid too large");
   const int nblocks = (int)((d.ncells + kThreads - 1) / kThreads);
   mc_case_kernel<<<nblocks, kThreads, 0, (cudaStream_t)stream>>>(grid, d, level, case_out);
   R3G_LAUNCH_OK(ctx);
