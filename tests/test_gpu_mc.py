@@ -44,6 +44,21 @@ def test_mc_bit_exact(name, vol):
         assert np.array_equal(ops.mc_classify(g, level).cpu().numpy(), oc), f"{name}: cell cases differ"
 
 
+def test_mc_unaligned_grid_pointer():
+    """A grid whose base is not 16-byte aligned takes the scalar-load variant of the sign-bit pass: same mesh."""
+    import mc as omc
+    from r3g import ops
+    from test_mc_oracle import random_field
+    vol = random_field(33, 5)
+    ov, of = omc.marching_cubes(vol, 0.0)[:2]
+    flat = torch.empty(vol.size + 1, device="cuda")
+    g = flat[1:].view(vol.shape)
+    g.copy_(torch.from_numpy(vol))
+    assert g.data_ptr() % 16 != 0 and g.is_contiguous()
+    v, f = ops.marching_cubes(g, 0.0)
+    assert np.array_equal(f.cpu().numpy(), of) and np.array_equal(v.cpu().numpy(), ov)
+
+
 def test_mc_errors_match_skimage_behaviour():
     from r3g import ops
     from test_mc_oracle import sphere
