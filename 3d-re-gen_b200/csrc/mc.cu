@@ -517,13 +517,20 @@ __global__ void __launch_bounds__(kThreads) mc_vertex_kernel(const float* __rest
     }
     unsigned id = block_offsets[kb].x + excl[0];
     const int t0 = r3g_mc_tiling_start[til], t1 = r3g_mc_tiling_start[til + 1];
+    // the edges this cell owns, in first-use order of its tiling (4 bits each; at most 13): integer work only, so that the
+    // float64 part below runs max-over-the-warp(nv) times, not once per tiling position at which some lane owns an edge
+    unsigned long long owned = 0;
     unsigned seen = 0;
+    int n = 0;
     for (int t = t0; t < t1; ++t) {
       const int e = r3g_mc_tri[t];
       const unsigned bit = 1u << e;
       if (seen & bit) continue;
       seen |= bit;
-      if (!(e == 12 || owns_edge(e, x, y, z))) continue;
+      if (e == 12 || owns_edge(e, x, y, z)) { owned |= (unsigned long long)e << (4 * n); ++n; }
+    }
+    for (int k = 0; k < n; ++k) {
+      const int e = (int)((owned >> (4 * k)) & 15ull);
       double fx = 0, fy = 0, fz = 0, ff = 0;
       if (e == 12) {
 #pragma unroll

@@ -51,8 +51,10 @@ int64_t r3g_launch_count(r3g_ctx* ctx);
  *                    (Hunyuan3D-2/hy3dgen/shapegen/pipelines.py:102).  If bounds_host != NULL (6 doubles:
  *                    min xyz, max xyz) vertices are rescaled v / n_axis * (max-min) + min in float64 and
  *                    stored float32, as surface_extractors.py:74-75,55 do.
- * workspace: r3g_mc_workspace_bytes(n0,n1,n2) bytes of device memory, contents need not be initialised;
- *            the same workspace must be passed to count and extract.
+ * workspace: r3g_mc_workspace_bytes(n0,n1,n2) bytes of device memory (about 23 bytes per grid point: 0.39 GB at
+ *            257^3, 3.0 GB at 513^3; sized for the worst case of every cell crossed), contents need not be
+ *            initialised; the same workspace must be passed to count and extract.
+ * Limits: (n0-1)*(n1-1)*ceil((n2-1)/32) < 2^27 (about 1600^3), else R3G_E_INVALID.
  */
 size_t r3g_mc_workspace_bytes(int n0, int n1, int n2);
 int r3g_mc_count(r3g_ctx* ctx, const float* grid, int n0, int n1, int n2, float level, void* workspace,
