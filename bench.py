@@ -151,7 +151,7 @@ def shapegen_config(args, world, per_rank):
     return {"workload": workload_name(args), "octree_resolution": args.octree, "dit_steps": args.dit_steps,
             "guidance": 5.0, "objects_per_gpu": per_rank, "objects_total": per_rank * world,
             "l2": "working set (2.6 GB of weights + a 68-540 MB grid per object) exceeds L2",
-            "parallelism": f"objects sharded over {world} GPU(s), meshes streamed to rank 0 over NCCL"}
+            "parallelism": f"objects sharded over {world} GPU(s), meshes gathered to rank 0 over NCCL"}
 
 
 def reference_arm(args):
