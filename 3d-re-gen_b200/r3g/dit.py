@@ -12,7 +12,6 @@ Data layout in HBM (per forward, B = 2 for classifier-free guidance):
   mods  [B, sum(mod widths)]     every block's Modulation.lin output from ONE gemv per forward
 All GEMMs / attention run on tcgen05 (gemm.cu, attn.cu); LayerNorm+modulation, q/k RMS-norm are row kernels.
 """
-import math
 
 import torch
 
