@@ -50,6 +50,20 @@ def test_compute_fails_loudly_without_gpu(lib):
     assert lib.r3g_version() >= 100
 
 
+def test_marching_cubes_workspace_size(lib):
+    """r3g_mc_workspace_bytes is pure arithmetic (no device): it covers 16 B of vertex-id slots per grid point plus the
+    sign bits, the crossed-cell list and the info words sized for every cell; degenerate grids give 0."""
+    assert lib.r3g_mc_workspace_bytes(1, 9, 9) == 0
+    prev = 0
+    for n in (2, 9, 33, 65, 257, 513):
+        b = lib.r3g_mc_workspace_bytes(n, n, n)
+        assert b % 256 == 0 and b > prev
+        assert b >= 16 * n ** 3 + n ** 3 // 8 + 6 * (n - 1) ** 3
+        assert b <= 1.05 * (16 * n ** 3 + n ** 3 // 8 + 6 * (n - 1) ** 3) + (1 << 20)      # + masks, scan arrays, alignment
+        prev = b
+    assert lib.r3g_mc_workspace_bytes(7, 12, 9) > 0
+
+
 def test_product_package_does_not_import_oracle():
     pkg = os.path.join(ROOT, "3d-re-gen_b200")
     for dp, _, files in os.walk(pkg):
